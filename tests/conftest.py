@@ -1,0 +1,33 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "warp-transducer_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def known_answers():
+    import json
+    return json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+
+
+@pytest.fixture(scope="session")
+def ref_cases():
+    z = np.load(os.path.join(GOLDEN, "ref_cases.npz"))
+    cases = {}
+    for name in z["names"]:
+        name = str(name)
+        cases[name] = {k.split(".", 1)[1]: z[k] for k in z.files if k.startswith(name + ".")}
+    return cases
