@@ -1,0 +1,161 @@
+/*
+ * rnnt.h — C-ABI of the B200-native RNN-Transducer loss (libwarprnnt.so).
+ *
+ * Binary drop-in for the reference library's interface: the same five exported symbols, the
+ * same enum values and the same 32-byte by-value options struct, so anything that links the
+ * reference (its PyTorch / TensorFlow bindings, tests/*.cu) links this instead.  Each
+ * declaration names the reference interface it replaces (paths relative to the reference
+ * checkout).  Only the CUDA device path exists here: there is no CPU implementation behind
+ * this ABI (see `loc` below).
+ *
+ * All tensors are dense, row-major, no padding between dimensions:
+ *   activations / gradients  [minibatch, maxT, maxU, alphabet_size]
+ *   flat_labels              [minibatch, maxU - 1]   (padded to maxU-1 per utterance)
+ *   label_lengths, input_lengths, costs  [minibatch]
+ */
+#ifndef B200_RNNT_H_
+#define B200_RNNT_H_
+
+#ifdef __cplusplus
+#include <cstddef>
+extern "C" {
+#else
+#include <stdbool.h>
+#include <stddef.h>
+#endif
+
+/* Opaque CUDA stream handle (same forward declaration trick as reference include/rnnt.h:14). */
+typedef struct CUstream_st* CUstream;
+
+/* Return codes — values fixed by reference include/rnnt.h:16-22. */
+typedef enum {
+    RNNT_STATUS_SUCCESS = 0,
+    RNNT_STATUS_MEMOPS_FAILED = 1,    /* a cudaMemcpy/cudaMemset-class call failed            */
+    RNNT_STATUS_INVALID_VALUE = 2,    /* null pointer, non-positive dimension, unknown loc    */
+    RNNT_STATUS_EXECUTION_FAILED = 3, /* kernel launch/execution error, or loc == RNNT_CPU    */
+    RNNT_STATUS_UNKNOWN_ERROR = 4
+} rnntStatus_t;
+
+/* Replaces reference include/rnnt.h:25 (src/rnnt_entrypoint.cpp:14-16).  Returns 1: the
+ * reference's tests refuse to run against any other value (tests/test_cpu.cpp:382-385). */
+int get_warprnnt_version(void);
+
+/* Replaces reference include/rnnt.h:31 (src/rnnt_entrypoint.cpp:18-35).  Static strings. */
+const char* rnntGetStatusString(rnntStatus_t status);
+
+/* Reference include/rnnt.h:33-36. */
+typedef enum {
+    RNNT_CPU = 0, /* not available in this library: compute calls return EXECUTION_FAILED */
+    RNNT_GPU = 1
+} rnntComputeLocation;
+
+/*
+ * Options, passed BY VALUE.  Layout fixed by reference include/rnnt.h:43-64
+ * (x86-64: 32 bytes, offsets 0/4/8/16/20/24/28).  Zero-initialise before filling.
+ */
+struct rnntOptions {
+    rnntComputeLocation loc;  /* must be RNNT_GPU                                              */
+    unsigned int num_threads; /* accepted and ignored (no host threading on the device path)  */
+    CUstream stream;          /* all device work is enqueued here                              */
+    int blank_label;          /* index of the blank symbol                                     */
+    int maxT;                 /* time extent of the activation tensor                          */
+    int maxU;                 /* label extent of the activation tensor (max label length + 1) */
+    bool batch_first;         /* ignored: the device path is always [N,T,U,V], as the
+                                 reference's GPU path is (include/detail/gpu_rnnt_kernel.h:7) */
+};
+#ifndef __cplusplus
+typedef struct rnntOptions rnntOptions;
+#endif
+
+/*
+ * RNN-T negative log-likelihood per utterance and, optionally, its gradient with respect to
+ * the raw logits.  Replaces reference include/rnnt.h:104-113 (src/rnnt_entrypoint.cpp:38-93)
+ * for loc == RNNT_GPU, with the GPU path's conventions (include/detail/gpu_rnnt.h:82-215):
+ *
+ *   activations   DEVICE, raw (un-normalised) logits; log-softmax over the last axis is
+ *                 computed inside.
+ *   gradients     DEVICE, same shape, or NULL for loss only.  When non-NULL every element is
+ *                 defined on return: d cost[b] / d logit for valid cells, 0 for padded cells
+ *                 (t >= input_lengths[b] or u > label_lengths[b]).  Not scaled or reduced.
+ *   flat_labels, label_lengths, input_lengths
+ *                 DEVICE pointers, as every caller of the reference's GPU path passes them
+ *                 (tests/test_gpu.cu:54-59); HOST pointers are also accepted (detected with
+ *                 cudaPointerGetAttributes and staged through the workspace).
+ *   costs         HOST pointer (as the reference: D2H copy inside the call,
+ *                 include/detail/gpu_rnnt.h:209-213); a DEVICE pointer is accepted too.
+ *   workspace     DEVICE scratch of get_workspace_size(..., gpu=true, ...) bytes.
+ *
+ * The call returns after the stream has finished (costs are readable on return), like the
+ * reference.  Errors are reported by return code only; nothing is thrown across the ABI.
+ * Limits: minibatch*maxT*maxU < 2^31 cells (elements are indexed with 64 bits).
+ */
+rnntStatus_t compute_rnnt_loss(const float* const activations, float* gradients,
+                               const int* const flat_labels, const int* const label_lengths,
+                               const int* const input_lengths, int alphabet_size, int minibatch,
+                               float* costs, void* workspace, struct rnntOptions options);
+
+/* Double-precision twin.  Replaces reference include/rnnt.h:115-124
+ * (src/rnnt_entrypoint.cpp:130-185). */
+rnntStatus_t compute_rnnt_loss_fp64(const double* const activations, double* gradients,
+                                    const int* const flat_labels,
+                                    const int* const label_lengths,
+                                    const int* const input_lengths, int alphabet_size,
+                                    int minibatch, double* costs, void* workspace,
+                                    struct rnntOptions options);
+
+/*
+ * Scratch size in bytes.  Replaces reference include/rnnt.h:139-143
+ * (src/rnnt_entrypoint.cpp:96-128): same signature, same INVALID_VALUE rule for non-positive
+ * extents.  The byte count differs from the reference's (this library keeps a different
+ * lattice: see DESIGN.md "HBM layout"); callers always size through this function.
+ * gpu == false returns the reference's CPU formula for source compatibility only.
+ */
+#ifdef __cplusplus
+rnntStatus_t get_workspace_size(int maxT, int maxU, int minibatch, bool gpu, size_t* size_bytes,
+                                size_t dtype_size = sizeof(float));
+#else
+rnntStatus_t get_workspace_size(int maxT, int maxU, int minibatch, bool gpu, size_t* size_bytes,
+                                size_t dtype_size);
+#endif
+
+/* Same function under the name BASELINE.json's north_star uses (the reference has no such
+ * symbol; exported so either spelling links). */
+rnntStatus_t get_rnnt_workspace_size(int maxT, int maxU, int minibatch, bool gpu,
+                                     size_t* size_bytes, size_t dtype_size);
+
+/* ---------------------------------------------------------------------------------------
+ * Extensions (no reference counterpart).  Used by the warprnnt_pytorch operator to drop
+ * the framework-side passes SURVEY.md §8(f).1 lists, and by bench.py for device timing.
+ * ------------------------------------------------------------------------------------- */
+
+/*
+ * Asynchronous variant: identical computation, but
+ *   - costs_device [minibatch] is written on the DEVICE and the call does NOT synchronise;
+ *   - gradients are multiplied by grad_scale (pass 1.0f for the plain gradient): folds the
+ *     'mean' 1/N of warprnnt_pytorch/__init__.py:38-40 into the write-back.
+ * flat_labels/label_lengths/input_lengths must be DEVICE pointers here.
+ */
+rnntStatus_t compute_rnnt_loss_async(const float* const activations, float* gradients,
+                                     const int* const flat_labels,
+                                     const int* const label_lengths,
+                                     const int* const input_lengths, int alphabet_size,
+                                     int minibatch, float* costs_device, float grad_scale,
+                                     void* workspace, struct rnntOptions options);
+
+rnntStatus_t compute_rnnt_loss_async_fp64(const double* const activations, double* gradients,
+                                          const int* const flat_labels,
+                                          const int* const label_lengths,
+                                          const int* const input_lengths, int alphabet_size,
+                                          int minibatch, double* costs_device, double grad_scale,
+                                          void* workspace, struct rnntOptions options);
+
+/* Number of kernels the last compute call on this thread launched (bench.py's gpu_launches). */
+int rnnt_b200_last_launch_count(void);
+
+/* Build identification string, e.g. "b200-rnnt sm_100a <date>". */
+const char* rnnt_b200_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_RNNT_H_ */

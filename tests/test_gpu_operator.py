@@ -1,0 +1,120 @@
+"""warprnnt_pytorch operator surface on the GPU — reads like the reference's own
+pytorch_binding/test/test.py (small_test / big_test) plus reduction and autograd semantics."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+
+def wrap_and_call(fn, acts, labels, dtype=torch.float32):
+    """Mirror of pytorch_binding/test/test.py:27-48."""
+    acts = torch.tensor(acts, dtype=dtype).cuda()
+    acts.requires_grad = True
+    lengths = torch.IntTensor([acts.shape[1]] * acts.shape[0]).cuda()
+    label_lengths = torch.IntTensor([len(l) for l in labels]).cuda()
+    labels = torch.IntTensor(labels).cuda()
+    costs = fn(acts, labels, lengths, label_lengths)
+    cost = torch.sum(costs)
+    cost.backward()
+    return costs.data.cpu().numpy(), acts.grad.data.cpu().numpy()
+
+
+def test_small(known_answers):
+    from warprnnt_pytorch import RNNTLoss
+    ka = known_answers["small"]
+    acts = np.array(ka["acts"]).reshape(ka["shape"])
+    cost, grads = wrap_and_call(RNNTLoss(reduction='sum'), acts, ka["labels"])
+    assert np.allclose(cost, ka["cost"], rtol=1e-6)                       # test.py:75
+    assert np.allclose(grads.reshape(-1), ka["logits_grads"], atol=1e-6)   # test.py:77
+
+
+def test_big(known_answers):
+    from warprnnt_pytorch import RNNTLoss
+    ka = known_answers["options"]
+    acts = np.array(ka["acts_f64"]).reshape(ka["shape"])
+    costs, grads = wrap_and_call(RNNTLoss(reduction='sum'), acts, ka["labels"])
+    assert np.allclose(costs, sum(ka["costs"]))                            # test.py:155
+    assert np.allclose(grads.reshape(-1), ka["logits_grads_hi"], rtol=1e-3)  # test.py:158
+    costs, grads = wrap_and_call(RNNTLoss(reduction='sum'), acts, ka["labels"], torch.float64)
+    assert np.allclose(costs, sum(ka["costs"]), rtol=1e-12)
+    assert np.allclose(grads.reshape(-1), ka["logits_grads_hi"], rtol=1e-6)
+
+
+def test_reductions_and_grad_output():
+    from warprnnt_pytorch import RNNTLoss, rnnt_loss
+    rng = np.random.default_rng(1)
+    N, T, U, V = 5, 12, 6, 28
+    acts_np = rng.standard_normal((N, T, U, V)).astype(np.float32)
+    labels_np = rng.integers(1, V, size=(N, U - 1)).astype(np.int32)
+    tl_np = np.array([T, 9, 12, 7, 10], np.int32)
+    ul_np = np.array([U - 1, 2, 0, 5, 3], np.int32)
+    c_ref, g_ref, _ = pyoracle.rnnt_logits(acts_np.astype(np.float64), labels_np, tl_np, ul_np, 0)
+    labels, tl, ul = (torch.as_tensor(x).cuda() for x in (labels_np, tl_np, ul_np))
+
+    def run(reduction, weight=None):
+        acts = torch.tensor(acts_np, device="cuda", requires_grad=True)
+        out = RNNTLoss(reduction=reduction)(acts, labels, tl, ul)
+        assert out.is_cuda
+        if weight is None:
+            out.sum().backward()
+        else:
+            (out * weight).sum().backward()
+        return out.detach().cpu().numpy(), acts.grad.cpu().numpy()
+
+    out, g = run('none')
+    assert out.shape == (N,)
+    assert np.allclose(out, c_ref, rtol=1e-5) and np.allclose(g, g_ref, rtol=1e-4, atol=1e-6)
+    out, g = run('sum')
+    assert out.shape == (1,)
+    assert np.allclose(out, c_ref.sum(), rtol=1e-5) and np.allclose(g, g_ref, rtol=1e-4, atol=1e-6)
+    out, g = run('mean')      # reference: divides by the batch size (:36-40)
+    assert np.allclose(out, c_ref.sum() / N, rtol=1e-5)
+    assert np.allclose(g, g_ref / N, rtol=1e-4, atol=1e-6)
+    w = torch.tensor([1.0, -2.0, 0.5, 3.0, 0.0], device="cuda")
+    out, g = run('none', w)   # per-utterance upstream gradient (backward :47-50)
+    assert np.allclose(g, g_ref * w.cpu().numpy()[:, None, None, None], rtol=1e-4, atol=1e-6)
+    # functional form, default reduction 'mean', no grad required -> loss only
+    acts = torch.tensor(acts_np, device="cuda")
+    out = rnnt_loss(acts, labels, tl, ul)
+    assert np.allclose(out.cpu().numpy(), c_ref.sum() / N, rtol=1e-5)
+
+
+def test_blank_argument():
+    from warprnnt_pytorch import RNNTLoss
+    rng = np.random.default_rng(2)
+    N, T, U, V = 2, 6, 4, 9
+    acts_np = rng.standard_normal((N, T, U, V)).astype(np.float32)
+    blank = V - 1
+    labels_np = rng.integers(0, V - 1, size=(N, U - 1)).astype(np.int32)
+    tl_np, ul_np = np.full(N, T, np.int32), np.full(N, U - 1, np.int32)
+    c_ref, g_ref, _ = pyoracle.rnnt_logits(acts_np.astype(np.float64), labels_np, tl_np, ul_np, blank)
+    acts = torch.tensor(acts_np, device="cuda", requires_grad=True)
+    out = RNNTLoss(blank=blank, reduction='none')(acts, *(torch.as_tensor(x).cuda() for x in (labels_np, tl_np, ul_np)))
+    out.sum().backward()
+    assert np.allclose(out.detach().cpu().numpy(), c_ref, rtol=1e-5)
+    assert np.allclose(acts.grad.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)
+
+
+def test_reference_style_gpu_rnnt_call():
+    """The raw extension call the reference's autograd function makes (__init__.py:22-34):
+    CPU costs tensor, zero-initialised grads, returns 0."""
+    from warprnnt_pytorch import warp_rnnt
+    rng = np.random.default_rng(3)
+    N, T, U, V = 3, 8, 4, 28
+    acts_np = rng.random((N, T, U, V)).astype(np.float32)
+    labels_np = rng.integers(1, V, size=(N, U - 1)).astype(np.int32)
+    tl_np, ul_np = np.full(N, T, np.int32), np.full(N, U - 1, np.int32)
+    acts = torch.tensor(acts_np).cuda()
+    grads = torch.zeros_like(acts)
+    costs = torch.zeros(N)
+    rc = warp_rnnt.gpu_rnnt(acts, *(torch.as_tensor(x).cuda() for x in (labels_np, tl_np, ul_np)),
+                            costs, grads, 0, 0)
+    assert rc == 0
+    c_ref, g_ref, _ = pyoracle.rnnt_logits(acts_np.astype(np.float64), labels_np, tl_np, ul_np, 0)
+    assert np.allclose(costs.numpy(), c_ref, rtol=1e-5)
+    assert np.allclose(grads.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        warp_rnnt.cpu_rnnt(acts.cpu(), None, None, None, costs, grads.cpu(), 0, 0)

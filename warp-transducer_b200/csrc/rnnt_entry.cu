@@ -1,0 +1,324 @@
+// rnnt_entry.cu — C-ABI of libwarprnnt.so (declared in include/rnnt.h) and the host-side
+// orchestration of the three kernels.  Replaces reference src/rnnt_entrypoint.cpp and
+// include/detail/gpu_rnnt.h (GpuRNNT<T>::compute_cost_and_score) for loc == RNNT_GPU.
+//
+// Per call, on options.stream:  [stage host labels/lengths if needed] -> rowstats -> lattice
+// (alpha || beta) -> grad -> costs to host + ONE stream synchronise (sync API) / nothing (async API).
+// No memset pass, no intermediate host synchronisation.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include <cuda_runtime.h>
+
+#include "../../include/rnnt.h"
+#include "rnnt_kernels.cuh"
+
+using namespace b200rnnt;
+
+namespace {
+
+thread_local int g_last_launches = 0;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- workspace carve-up (all sections 256-B aligned) -------------------------------------------
+struct Workspace {
+    void* stat;     // pair<T>  [rows]   (row max, log sum exp)
+    void* lp2;      // pair<T>  [rows]   (blank, label) log-probs
+    double* alphas; // [rows]
+    double* betas;  // [rows]
+    double* llf;    // [N]
+    double* llb;    // [N]
+    void* costs;    // T [N]
+    int* labels;    // staging for host-side integer inputs
+    int* ylen;
+    int* xlen;
+    size_t bytes;
+};
+
+Workspace carve(void* base, size_t rows, int N, int maxU, size_t dtype) {
+    Workspace w;
+    size_t off = align_up(reinterpret_cast<uintptr_t>(base), 256) - reinterpret_cast<uintptr_t>(base);
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t n) {
+        void* q = p ? p + off : nullptr;
+        off = align_up(off + n, 256);
+        return q;
+    };
+    w.stat = take(rows * 2 * dtype);
+    w.lp2 = take(rows * 2 * dtype);
+    w.alphas = static_cast<double*>(take(rows * sizeof(double)));
+    w.betas = static_cast<double*>(take(rows * sizeof(double)));
+    w.llf = static_cast<double*>(take(N * sizeof(double)));
+    w.llb = static_cast<double*>(take(N * sizeof(double)));
+    w.costs = take(N * dtype);
+    w.labels = static_cast<int*>(take((size_t)N * (maxU > 1 ? maxU - 1 : 1) * sizeof(int)));
+    w.ylen = static_cast<int*>(take(N * sizeof(int)));
+    w.xlen = static_cast<int*>(take(N * sizeof(int)));
+    w.bytes = off + 256;  // slack for a base pointer that is not 256-aligned
+    return w;
+}
+
+struct DeviceInfo {
+    int sms = 0;
+};
+const DeviceInfo& device_info() {
+    thread_local int cached_dev = -1;
+    thread_local DeviceInfo info;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&info.sms, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return info;
+}
+
+bool is_device_pointer(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+template <typename K> int blocks_for(K kernel, int threads, int sms) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * sms;
+}
+
+// ---- streaming-kernel dispatch on (vector width, lanes per row) ---------------------------------
+template <typename T, int VEC, int LPR, int UNR>
+void launch_rowstats(const T* acts, const int* labels, const int* xlen, const int* ylen,
+                     const Workspace& w, const Dims& d, cudaStream_t s, int sms) {
+    auto k = rowstats_kernel<T, VEC, LPR, UNR>;
+    static thread_local int blocks = 0;
+    if (!blocks) blocks = blocks_for(k, 256, sms);
+    const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;  // warps of work
+    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks);
+    k<<<grid, 256, 0, s>>>(acts, labels, xlen, ylen,
+                           static_cast<typename Real<T>::pair*>(w.stat),
+                           static_cast<typename Real<T>::pair*>(w.lp2), d);
+    ++g_last_launches;
+}
+
+template <typename T, int VEC, int LPR, int UNR>
+void launch_grad(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+                 const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms) {
+    auto k = grad_kernel<T, VEC, LPR, UNR>;
+    static thread_local int blocks = 0;
+    if (!blocks) blocks = blocks_for(k, 256, sms);
+    const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;
+    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks);
+    k<<<grid, 256, 0, s>>>(acts, grads, labels, xlen, ylen,
+                           static_cast<const typename Real<T>::pair*>(w.stat), w.alphas, w.betas,
+                           w.llf, scale, d);
+    ++g_last_launches;
+}
+
+template <typename T, int VEC>
+void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+                   const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms, int pass) {
+    const int nv = d.V / VEC;
+    if (nv <= 8) {
+        if (pass == 1) launch_rowstats<T, VEC, 8, 1>(acts, labels, xlen, ylen, w, d, s, sms);
+        else launch_grad<T, VEC, 8, 1>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+    } else if (nv <= 64) {
+        if (pass == 1) launch_rowstats<T, VEC, 32, 1>(acts, labels, xlen, ylen, w, d, s, sms);
+        else launch_grad<T, VEC, 32, 1>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+    } else {
+        if (pass == 1) launch_rowstats<T, VEC, 32, 4>(acts, labels, xlen, ylen, w, d, s, sms);
+        else launch_grad<T, VEC, 32, 4>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+    }
+}
+
+template <typename T>
+void stream_pass(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+                 const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms, int pass) {
+    // widest vector the row pitch and the base pointers allow
+    const uintptr_t mis = reinterpret_cast<uintptr_t>(acts) | reinterpret_cast<uintptr_t>(grads) |
+                          ((uintptr_t)d.V * sizeof(T));
+    constexpr int kMaxVec = 16 / sizeof(T);
+    if (mis % 16 == 0)
+        stream_passes<T, kMaxVec>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, pass);
+    else if (sizeof(T) == 4 && mis % 8 == 0)
+        stream_passes<T, (kMaxVec > 2 ? 2 : 1)>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, pass);
+    else
+        stream_passes<T, 1>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, pass);
+}
+
+// ---- the path -----------------------------------------------------------------------------------
+template <typename T>
+rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, const int* xlen,
+                 int V, int N, T* costs, bool async, T scale, void* workspace, rnntOptions opt) {
+    if (acts == nullptr || labels == nullptr || ylen == nullptr || xlen == nullptr ||
+        costs == nullptr || workspace == nullptr || V <= 0 || N <= 0 || opt.maxT <= 0 ||
+        opt.maxU <= 0)
+        return RNNT_STATUS_INVALID_VALUE;  // reference src/rnnt_entrypoint.cpp:49-59
+    if (opt.loc == RNNT_CPU) {
+        fprintf(stderr, "b200-rnnt: CPU execution requested, but this library is the CUDA path only\n");
+        return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    if (opt.loc != RNNT_GPU) return RNNT_STATUS_INVALID_VALUE;  // :90-92
+    const uint64_t rows64 = (uint64_t)N * opt.maxT * opt.maxU;
+    if (rows64 >= (1ull << 31) || opt.maxU > 1024 * 1024 || opt.blank_label < 0 || opt.blank_label >= V)
+        return RNNT_STATUS_INVALID_VALUE;
+    if (opt.maxU > 1024) {
+        fprintf(stderr, "b200-rnnt: maxU > 1024 is not supported (the reference launches maxU threads per block and has the same limit)\n");
+        return RNNT_STATUS_INVALID_VALUE;
+    }
+
+    g_last_launches = 0;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(opt.stream);
+    const int sms = device_info().sms;
+    Workspace w = carve(workspace, rows64, N, opt.maxU, sizeof(T));
+
+    Dims d;
+    d.N = N;
+    d.maxT = opt.maxT;
+    d.maxU = opt.maxU;
+    d.V = V;
+    d.blank = opt.blank_label;
+    d.rows = (uint32_t)rows64;
+    d.divU = FastDiv(opt.maxU);
+    d.divT = FastDiv(opt.maxT);
+
+    // Integer inputs: device pointers are used in place; host pointers (the header's literal
+    // contract, reference include/rnnt.h:84-89) are staged through the workspace.
+    if (!async) {
+        const size_t nl = (size_t)N * (opt.maxU > 1 ? opt.maxU - 1 : 0);
+        if (!is_device_pointer(labels)) {
+            if (nl && cudaMemcpyAsync(w.labels, labels, nl * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess)
+                return RNNT_STATUS_MEMOPS_FAILED;
+            labels = w.labels;
+        }
+        if (!is_device_pointer(ylen)) {
+            if (cudaMemcpyAsync(w.ylen, ylen, N * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess)
+                return RNNT_STATUS_MEMOPS_FAILED;
+            ylen = w.ylen;
+        }
+        if (!is_device_pointer(xlen)) {
+            if (cudaMemcpyAsync(w.xlen, xlen, N * sizeof(int), cudaMemcpyHostToDevice, s) != cudaSuccess)
+                return RNNT_STATUS_MEMOPS_FAILED;
+            xlen = w.xlen;
+        }
+    }
+
+    // pass 1: log-softmax statistics + (blank, label) log-prob gather
+    stream_pass<T>(acts, nullptr, labels, xlen, ylen, w, scale, d, s, sms, 1);
+
+    // lattice: alpha (and beta when gradients are wanted), one CTA per (utterance, direction)
+    {
+        const int threads = (opt.maxU + 31) / 32 * 32;
+        dim3 grid(N, grads ? 2 : 1);
+        T* cdev = async ? costs : static_cast<T*>(w.costs);
+        if (threads > 32)
+            lattice_kernel<T, true><<<grid, threads, 0, s>>>(
+                static_cast<const typename Real<T>::pair*>(w.lp2), xlen, ylen, w.alphas, w.betas,
+                w.llf, w.llb, cdev, d);
+        else
+            lattice_kernel<T, false><<<grid, threads, 0, s>>>(
+                static_cast<const typename Real<T>::pair*>(w.lp2), xlen, ylen, w.alphas, w.betas,
+                w.llf, w.llb, cdev, d);
+        ++g_last_launches;
+    }
+
+    // pass 2: dense gradient (+ zeros on padding)
+    if (grads) stream_pass<T>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, 2);
+
+    if (cudaGetLastError() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+    if (async) return RNNT_STATUS_SUCCESS;
+
+    // costs to the caller (host memory in the reference contract) and the call's single sync
+    const cudaMemcpyKind kind = is_device_pointer(costs) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (cudaMemcpyAsync(costs, w.costs, N * sizeof(T), kind, s) != cudaSuccess)
+        return RNNT_STATUS_MEMOPS_FAILED;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+    return RNNT_STATUS_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int get_warprnnt_version(void) { return 1; }
+
+const char* rnntGetStatusString(rnntStatus_t status) {
+    switch (status) {
+        case RNNT_STATUS_SUCCESS: return "no error";
+        case RNNT_STATUS_MEMOPS_FAILED: return "cuda memcpy or memset failed";
+        case RNNT_STATUS_INVALID_VALUE: return "invalid value";
+        case RNNT_STATUS_EXECUTION_FAILED: return "execution failed";
+        case RNNT_STATUS_UNKNOWN_ERROR:
+        default: return "unknown error";
+    }
+}
+
+rnntStatus_t compute_rnnt_loss(const float* const activations, float* gradients,
+                               const int* const flat_labels, const int* const label_lengths,
+                               const int* const input_lengths, int alphabet_size, int minibatch,
+                               float* costs, void* workspace, rnntOptions options) {
+    return run<float>(activations, gradients, flat_labels, label_lengths, input_lengths,
+                      alphabet_size, minibatch, costs, false, 1.0f, workspace, options);
+}
+
+rnntStatus_t compute_rnnt_loss_fp64(const double* const activations, double* gradients,
+                                    const int* const flat_labels,
+                                    const int* const label_lengths,
+                                    const int* const input_lengths, int alphabet_size,
+                                    int minibatch, double* costs, void* workspace,
+                                    rnntOptions options) {
+    return run<double>(activations, gradients, flat_labels, label_lengths, input_lengths,
+                       alphabet_size, minibatch, costs, false, 1.0, workspace, options);
+}
+
+rnntStatus_t compute_rnnt_loss_async(const float* const activations, float* gradients,
+                                     const int* const flat_labels,
+                                     const int* const label_lengths,
+                                     const int* const input_lengths, int alphabet_size,
+                                     int minibatch, float* costs_device, float grad_scale,
+                                     void* workspace, rnntOptions options) {
+    return run<float>(activations, gradients, flat_labels, label_lengths, input_lengths,
+                      alphabet_size, minibatch, costs_device, true, grad_scale, workspace, options);
+}
+
+rnntStatus_t compute_rnnt_loss_async_fp64(const double* const activations, double* gradients,
+                                          const int* const flat_labels,
+                                          const int* const label_lengths,
+                                          const int* const input_lengths, int alphabet_size,
+                                          int minibatch, double* costs_device, double grad_scale,
+                                          void* workspace, rnntOptions options) {
+    return run<double>(activations, gradients, flat_labels, label_lengths, input_lengths,
+                       alphabet_size, minibatch, costs_device, true, grad_scale, workspace, options);
+}
+
+rnntStatus_t get_workspace_size(int maxT, int maxU, int minibatch, bool gpu, size_t* size_bytes,
+                                size_t dtype_size) {
+    if (minibatch <= 0 || maxT <= 0 || maxU <= 0 || size_bytes == nullptr)
+        return RNNT_STATUS_INVALID_VALUE;  // reference src/rnnt_entrypoint.cpp:102-105
+    if (dtype_size != sizeof(double)) dtype_size = sizeof(float);
+    const size_t rows = (size_t)minibatch * maxT * maxU;
+    if (!gpu) {
+        // No CPU path here; the reference's figure (alphas, betas, 2-wide log-prob cache) is
+        // returned so host-side sizing code keeps working.  src/rnnt_entrypoint.cpp:113-118
+        *size_bytes = dtype_size * rows * 4;
+        return RNNT_STATUS_SUCCESS;
+    }
+    *size_bytes = carve(nullptr, rows, minibatch, maxU, dtype_size).bytes;
+    return RNNT_STATUS_SUCCESS;
+}
+
+rnntStatus_t get_rnnt_workspace_size(int maxT, int maxU, int minibatch, bool gpu,
+                                     size_t* size_bytes, size_t dtype_size) {
+    return get_workspace_size(maxT, maxU, minibatch, gpu, size_bytes, dtype_size);
+}
+
+int rnnt_b200_last_launch_count(void) { return g_last_launches; }
+
+const char* rnnt_b200_build_info(void) { return "b200-rnnt sm_100a built " __DATE__ " " __TIME__; }
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+// rnnt_kernels.cuh — the three sm_100a kernels of the RNN-T loss + gradient path.
+//
+//   rowstats_kernel  pass 1 over the logits [N,T,U,V]: per lattice cell the log-softmax statistics
+//                    (row max m, log sum exp(x-m)) and the two log-probs the lattice needs
+//                    (blank, label y_u).      replaces reference reduce_max + reduce_exp
+//                    (include/detail/reduce.h:45-146, gpu_rnnt.h:73-80) and the per-step logp()
+//                    gathers (gpu_rnnt_kernel.h:5-9); analogue of CpuRNNT setup_probs (cpu_rnnt.h:115-128)
+//   lattice_kernel   alpha and beta anti-diagonal wavefronts, one CTA per (utterance, direction),
+//                    one thread per u, running concurrently.   replaces compute_alphas_kernel /
+//                    compute_betas_kernel (gpu_rnnt_kernel.h:11-47,79-113)
+//   grad_kernel      pass 2 over the logits: dense gradient w.r.t. logits, zeros on padded cells.
+//                    replaces cudaMemsetAsync + compute_grad_kernel (gpu_rnnt.h:107-110,
+//                    gpu_rnnt_kernel.h:143-179)
+//
+// HBM traffic: 4 B/elt (pass 1) + 8 B/elt (pass 2) + ~(16+16+16) B per lattice cell.
+#pragma once
+#include "rnnt_common.cuh"
+
+namespace b200rnnt {
+
+struct Dims {
+    int N, maxT, maxU, V, blank;
+    uint32_t rows;  // N*maxT*maxU  (< 2^31)
+    FastDiv divU, divT;
+};
+
+// clamp the per-utterance extents into the tensor so corrupt lengths cannot index outside it
+__device__ __forceinline__ void utt_extent(const Dims& d, const int* __restrict__ xlen,
+                                           const int* __restrict__ ylen, int b, int& T, int& U) {
+    T = min(max(__ldg(xlen + b), 1), d.maxT);
+    U = min(max(__ldg(ylen + b) + 1, 1), d.maxU);
+}
+
+// =================================================================================================
+// Pass 1: row statistics.
+// A row (one lattice cell's V logits) is owned by an aligned group of LPR lanes; a warp owns
+// 32/LPR consecutive rows, so a warp-wide load instruction covers one contiguous span of memory
+// (coalesced) for any V.  LPR = 32: one row per warp, UNR independent 16-B loads in flight per lane.
+// Each lane keeps an online (max, sum) pair and rescales only when its running max moves.
+// =================================================================================================
+template <typename T, int VEC, int LPR, int UNR>
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
+                const int* __restrict__ xlen, const int* __restrict__ ylen,
+                typename Real<T>::pair* __restrict__ stat, typename Real<T>::pair* __restrict__ lp2,
+                const Dims d) {
+    using R = Real<T>;
+    constexpr int RPW = kWarp / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = d.V / VEC;
+
+    for (uint64_t r0 = (uint64_t)gw * RPW; r0 < d.rows; r0 += (uint64_t)warps_total * RPW) {
+        const uint32_t r = (uint32_t)r0 + sub;
+        bool valid = r < d.rows;
+        uint32_t bt = 0, u = 0, b = 0, t = 0;
+        int Tb = 0, Ub = 0;
+        if (valid) {
+            d.divU.divmod(r, bt, u);
+            d.divT.divmod(bt, b, t);
+            utt_extent(d, xlen, ylen, b, Tb, Ub);
+            valid = (int)t < Tb && (int)u < Ub;
+        }
+        T m = R::neg_inf(), s = 0;
+        const T* row = acts + (uint64_t)r * d.V;
+        if (valid) {
+            for (int i0 = sl; i0 < nv; i0 += LPR * UNR) {
+                VecT<T, VEC> x[UNR];
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int i = i0 + j * LPR;
+                    if (i < nv) {
+                        x[j] = ld_keep<T, VEC>(row + (size_t)i * VEC);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) x[j].v[c] = R::neg_inf();
+                    }
+                }
+                T vm = x[0].v[0];
+#pragma unroll
+                for (int j = 0; j < UNR; ++j)
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) vm = x[j].v[c] > vm ? x[j].v[c] : vm;
+                if (vm > m) {  // running max moved: rescale the partial sum (rare after the first trips)
+                    s *= R::exp(m - vm);  // m = -inf -> exp(-inf) = 0, s was 0
+                    m = vm;
+                }
+                const T mm = (m == R::neg_inf()) ? T(0) : m;  // all -inf so far: keep exp() at 0, not NaN
+#pragma unroll
+                for (int j = 0; j < UNR; ++j)
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) s += R::exp(x[j].v[c] - mm);
+            }
+        }
+        // combine the LPR lanes of the row: global max first, one rescale per lane, then the sum
+        const T M = group_max<LPR>(m);
+        const T sc = (m == R::neg_inf()) ? T(0) : s * R::exp(m - M);
+        const T S = group_sum<LPR>(sc);
+        if (valid && sl == 0) {
+            const T lse = R::log(S);
+            typename R::pair st;
+            st.x = M;
+            st.y = lse;
+            stat[r] = st;
+            typename R::pair lp;
+            lp.x = (__ldg(row + d.blank) - M) - lse;
+            lp.y = 0;
+            if ((int)u < Ub - 1) {
+                const int y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+                lp.y = (__ldg(row + y) - M) - lse;
+            }
+            lp2[r] = lp;
+        }
+    }
+}
+
+// =================================================================================================
+// Lattice DP.  grid = (N, 2): blockIdx.y 0 -> alpha (forward), 1 -> beta (backward); the two
+// directions of an utterance run concurrently on different SMs.  One thread per u; anti-diagonal
+// n = t + u is the step index, so thread u handles cell (n - u, u) at step n.  The u-1 (u+1)
+// neighbour's value comes by warp shuffle; across warps through a double-buffered shared slot
+// and ONE __syncthreads per diagonal (none when maxU <= 32).  The (blank,label) log-probs of the
+// next PF diagonals are prefetched into registers, so the dependent chain per step is
+//   shuffle -> DADD -> max/min -> ex2 -> lg2 -> DADD.
+// alpha/beta are carried and stored in double (see lse_step).
+// =================================================================================================
+template <typename T, bool MULTI>
+__global__ void __launch_bounds__(1024)
+lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __restrict__ xlen,
+               const int* __restrict__ ylen, double* __restrict__ alphas,
+               double* __restrict__ betas, double* __restrict__ llf, double* __restrict__ llb,
+               T* __restrict__ costs, const Dims d) {
+    constexpr int PF = 4;
+    constexpr double NINF = -(double)INFINITY;
+    __shared__ double edge[2][32];
+    const int b = blockIdx.x;
+    const int u = threadIdx.x;
+    const int lane = u & 31, warp = u >> 5;
+    const int nwarps = blockDim.x >> 5;
+    int Tb, Ub;
+    utt_extent(d, xlen, ylen, b, Tb, Ub);
+    const size_t base = (size_t)b * d.maxT * d.maxU;
+    const typename Real<T>::pair* lp = lp2 + base;
+    const int last = Tb + Ub - 2;
+    const bool mine = u < Ub;
+    const int mU = d.maxU;
+
+    if (blockIdx.y == 0) {
+        // ------------------------------------------------------------------ alpha
+        double* al = alphas + base;
+        double a = (u == 0) ? 0.0 : NINF;  // alpha(t-1, u) of this thread's column
+        if (u == 0) al[0] = 0.0;
+        T sx[PF], ey[PF];
+        auto fetch = [&](int n, T& s_, T& e_) {
+            const int t = n - u;
+            s_ = 0;
+            e_ = 0;
+            if (mine && n <= last && t >= 0 && t < Tb) {
+                if (t > 0) s_ = __ldg(&lp[(size_t)(t - 1) * mU + u].x);
+                if (u > 0) e_ = __ldg(&lp[(size_t)t * mU + u - 1].y);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < PF; ++j) fetch(1 + j, sx[j], ey[j]);
+        for (int n0 = 1; n0 <= last; n0 += PF) {
+#pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                const int n = n0 + j;
+                if (n <= last) {  // block-uniform
+                    if (MULTI) {
+                        if (lane == 31) edge[n & 1][warp] = a;
+                        __syncthreads();
+                    }
+                    double a_left = __shfl_up_sync(0xffffffffu, a, 1);
+                    if (MULTI && lane == 0) a_left = warp > 0 ? edge[n & 1][warp - 1] : NINF;
+                    const int t = n - u;
+                    if (mine && t >= 0 && t < Tb) {
+                        const double stay = t > 0 ? a + (double)sx[j] : NINF;
+                        const double emit = u > 0 ? a_left + (double)ey[j] : NINF;
+                        a = lse_step<T>(stay, emit);
+                        al[(size_t)t * mU + u] = a;
+                    }
+                    fetch(n + PF, sx[j], ey[j]);
+                }
+            }
+        }
+        if (u == Ub - 1) {
+            const double ll = a + (double)__ldg(&lp[(size_t)(Tb - 1) * mU + Ub - 1].x);
+            llf[b] = ll;
+            costs[b] = (T)(-ll);
+        }
+    } else {
+        // ------------------------------------------------------------------ beta
+        double* be = betas + base;
+        double bv = NINF;  // beta(t+1, u) of this thread's column
+        T px[PF], py[PF];
+        auto fetch = [&](int n, T& x_, T& y_) {
+            const int t = n - u;
+            x_ = 0;
+            y_ = 0;
+            if (mine && n >= 0 && t >= 0 && t < Tb) {
+                const typename Real<T>::pair p = __ldg(&lp[(size_t)t * mU + u]);
+                x_ = p.x;
+                y_ = p.y;
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < PF; ++j) fetch(last - j, px[j], py[j]);
+        for (int n0 = last; n0 >= 0; n0 -= PF) {
+#pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                const int n = n0 - j;
+                if (n >= 0) {  // block-uniform
+                    if (MULTI) {
+                        if (lane == 0) edge[n & 1][warp] = bv;
+                        __syncthreads();
+                    }
+                    double b_right = __shfl_down_sync(0xffffffffu, bv, 1);
+                    if (MULTI && lane == 31) b_right = warp + 1 < nwarps ? edge[n & 1][warp + 1] : NINF;
+                    const int t = n - u;
+                    if (mine && t >= 0 && t < Tb) {
+                        if (t == Tb - 1 && u == Ub - 1) {
+                            bv = (double)px[j];
+                        } else {
+                            const double stay = t < Tb - 1 ? bv + (double)px[j] : NINF;
+                            const double emit = u < Ub - 1 ? b_right + (double)py[j] : NINF;
+                            bv = lse_step<T>(stay, emit);
+                        }
+                        be[(size_t)t * mU + u] = bv;
+                    }
+                    fetch(n - PF, px[j], py[j]);
+                }
+            }
+        }
+        if (u == 0) llb[b] = bv;
+    }
+}
+
+// =================================================================================================
+// Pass 2: dense gradient w.r.t. the logits, same row->lane mapping as pass 1, rows visited in
+// reverse so the tail of pass 1 is met first in L2.
+//   g_k = scale * ( e^{lp_k + alpha + beta - ll}
+//                   - [k = blank, t < T-1]        e^{lp_k + alpha + beta(t+1,u) - ll}
+//                   - [k = blank, t = T-1, u = U-1] e^{lp_k + alpha - ll}
+//                   - [k = y_u,  u < U-1]         e^{lp_k + alpha + beta(t,u+1) - ll} )
+// (reference gpu_rnnt_kernel.h:159-177), lp_k = (x_k - m) - lse.  The three per-row offsets are
+// formed once per row in double and rounded; per element the work is FADD, FFMA, MUFU.EX2, FMUL.
+// Padded rows are written as zeros here (no separate memset pass).
+// =================================================================================================
+template <typename T, int VEC, int LPR, int UNR>
+__global__ void __launch_bounds__(256)
+grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
+            const int* __restrict__ xlen, const int* __restrict__ ylen,
+            const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
+            const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
+            const Dims d) {
+    using R = Real<T>;
+    constexpr int RPW = kWarp / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = d.V / VEC;
+
+    for (uint64_t r0 = (uint64_t)gw * RPW; r0 < d.rows; r0 += (uint64_t)warps_total * RPW) {
+        const uint64_t rr = r0 + sub;
+        if (rr >= d.rows) continue;
+        const uint32_t r = d.rows - 1 - (uint32_t)rr;
+        uint32_t bt, u, b, t;
+        d.divU.divmod(r, bt, u);
+        d.divT.divmod(bt, b, t);
+        int Tb, Ub;
+        utt_extent(d, xlen, ylen, b, Tb, Ub);
+        const T* row = acts + (uint64_t)r * d.V;
+        T* grow = grads + (uint64_t)r * d.V;
+        if ((int)t >= Tb || (int)u >= Ub) {
+            VecT<T, VEC> z;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) z.v[c] = 0;
+            for (int i = sl; i < nv; i += LPR) st_stream<T, VEC>(grow + (size_t)i * VEC, z);
+            continue;
+        }
+        const typename R::pair st = __ldg(stat + r);
+        const double a = alphas[r];
+        const double occ = a - __ldg(llf + b);
+        const T m = st.x;
+        // offsets in the exp2 domain: 2^{(x-m)*log2e + c}
+        const T cA = ((T)(occ + betas[r]) - st.y) * R::kLog2e;
+        T cB = R::neg_inf(), cL = R::neg_inf();
+        if ((int)t < Tb - 1)
+            cB = ((T)(occ + betas[r + d.maxU]) - st.y) * R::kLog2e;
+        else if ((int)u == Ub - 1)
+            cB = ((T)occ - st.y) * R::kLog2e;
+        int y = -1;
+        if ((int)u < Ub - 1) {
+            cL = ((T)(occ + betas[r + 1]) - st.y) * R::kLog2e;
+            y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+        }
+        const int kb = d.blank;
+
+        for (int i0 = sl; i0 < nv; i0 += LPR * UNR) {
+            VecT<T, VEC> x[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int i = i0 + j * LPR;
+                if (i < nv) x[j] = ld_stream<T, VEC>(row + (size_t)i * VEC);
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int i = i0 + j * LPR;
+                if (i < nv) {
+                    const int k0 = i * VEC;
+                    VecT<T, VEC> g;
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) {
+                        const T dl = (x[j].v[c] - m) * R::kLog2e;
+                        T gv = R::exp2(dl + cA);
+                        if (k0 + c == kb) gv -= R::exp2(dl + cB);
+                        if (k0 + c == y) gv -= R::exp2(dl + cL);
+                        g.v[c] = gv * scale;
+                    }
+                    st_stream<T, VEC>(grow + (size_t)i * VEC, g);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace b200rnnt

@@ -1,0 +1,120 @@
+"""warprnnt_pytorch — RNN-T loss operator for PyTorch on the B200-native libwarprnnt.
+
+Same public surface as the reference package (pytorch_binding/warprnnt_pytorch/__init__.py):
+``RNNTLoss(blank=0, reduction='mean')``, ``rnnt_loss(acts, labels, act_lens, label_lens,
+blank=0, reduction='mean')`` and the ``warp_rnnt`` extension functions, with the reference's
+input rules and error types (certify_inputs, :115-140).  Differences, all on the fast side:
+the call never synchronises with the host except for the reference's own length check, costs
+stay on the device, no zeros_like / mul_ passes over the [N,T,U,V] gradient (the kernel writes
+every element, already scaled for 'mean').  CPU tensors are rejected: there is no host path.
+"""
+import torch
+from torch.autograd import Function
+from torch.nn import Module
+
+from . import warp_rnnt
+from .warp_rnnt import cpu_rnnt, gpu_rnnt, gpu_rnnt_async  # noqa: F401
+
+__all__ = ['rnnt_loss', 'RNNTLoss']
+
+
+class _RNNT(Function):
+    @staticmethod
+    def forward(ctx, acts, labels, act_lens, label_lens, blank, reduction):
+        """
+        acts: (batch x seqLength x labelLength x outputDim) raw joint-network logits
+        labels: (batch x maxLabelLength) int32 targets, zero padded
+        act_lens / label_lens: (batch) int32
+        """
+        certify_inputs(acts, labels, act_lens, label_lens)
+        if not acts.is_cuda:
+            raise RuntimeError("warprnnt_pytorch (B200 build) runs on CUDA tensors only; "
+                               "there is no CPU fallback")
+        if reduction not in ('none', 'sum', 'mean'):
+            raise ValueError("reduction must be 'none', 'sum' or 'mean'")
+        minibatch_size = acts.size(0)
+        need_grad = acts.requires_grad
+        grads = torch.empty_like(acts) if need_grad else None   # kernel defines every element
+        costs = torch.empty(minibatch_size, dtype=acts.dtype, device=acts.device)
+        # reference :38-40 divides costs and grads by N for 'mean'; the scale rides in the kernel
+        scale = 1.0 / minibatch_size if reduction == 'mean' else 1.0
+        ws = gpu_rnnt_async(acts, labels, act_lens, label_lens, costs, grads, blank, scale)
+        ctx.workspace = ws
+        if reduction in ('sum', 'mean'):
+            costs = costs.sum().unsqueeze_(-1)
+            if reduction == 'mean':
+                costs /= minibatch_size
+        ctx.grads = grads
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        # reference :47-50
+        grad_output = grad_output.view(-1, 1, 1, 1).to(ctx.grads)
+        return ctx.grads.mul_(grad_output), None, None, None, None, None
+
+
+def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction='mean'):
+    """RNN Transducer loss (reference :53-70).
+
+    reduction: 'none' | 'sum' | 'mean'; 'mean' divides the summed loss by the batch size (what
+    the reference computes, :36-40).
+    """
+    return _RNNT.apply(acts, labels, act_lens, label_lens, blank, reduction)
+
+
+class RNNTLoss(Module):
+    """Module form (reference :73-100): RNNTLoss(blank=0, reduction='mean')."""
+
+    def __init__(self, blank=0, reduction='mean'):
+        super(RNNTLoss, self).__init__()
+        self.blank = blank
+        self.reduction = reduction
+        self.loss = _RNNT.apply
+
+    def forward(self, acts, labels, act_lens, label_lens):
+        return self.loss(acts, labels, act_lens, label_lens, self.blank, self.reduction)
+
+
+def check_type(var, t, name):
+    if var.dtype is not t:
+        raise TypeError("{} must be {}".format(name, t))
+
+
+def check_contiguous(var, name):
+    if not var.is_contiguous():
+        raise ValueError("{} must be contiguous".format(name))
+
+
+def check_dim(var, dim, name):
+    if len(var.shape) != dim:
+        raise ValueError("{} must be {}D".format(name, dim))
+
+
+def certify_inputs(log_probs, labels, lengths, label_lengths):
+    """Input rules of the reference (:115-140): int32 labels/lengths, contiguous, 4-D acts,
+    2-D labels, T == max(lengths), U == max(label_lengths) + 1; TypeError / ValueError."""
+    check_type(labels, torch.int32, "labels")
+    check_type(label_lengths, torch.int32, "label_lengths")
+    check_type(lengths, torch.int32, "lengths")
+    check_contiguous(log_probs, "log_probs")
+    check_contiguous(labels, "labels")
+    check_contiguous(label_lengths, "label_lengths")
+    check_contiguous(lengths, "lengths")
+
+    if lengths.shape[0] != log_probs.shape[0]:
+        raise ValueError("must have a length per example.")
+    if label_lengths.shape[0] != log_probs.shape[0]:
+        raise ValueError("must have a label length per example.")
+
+    check_dim(log_probs, 4, "log_probs")
+    check_dim(labels, 2, "labels")
+    check_dim(lengths, 1, "lenghts")
+    check_dim(label_lengths, 1, "label_lenghts")
+    # one device->host transfer for both maxima (the reference pays two)
+    max_T, max_U = torch.stack((lengths.max(), label_lengths.max())).tolist()
+    T, U = log_probs.shape[1:3]
+    if T != max_T:
+        raise ValueError("Input length mismatch")
+    if U != max_U + 1:
+        raise ValueError("Output length mismatch")

@@ -1,0 +1,150 @@
+"""`warprnnt_pytorch.warp_rnnt` — the extension-module surface of the reference binding
+(pytorch_binding/src/binding.cpp:12-19,84-91,157-162), bound to libwarprnnt.so's C-ABI.
+
+    gpu_rnnt(acts, labels, input_lengths, label_lengths, costs, grads, blank_label, num_threads) -> int
+    cpu_rnnt(...)   raises: this build has no CPU path (and never falls back to one)
+
+The library is loaded eagerly; a missing or unloadable libwarprnnt.so is an ImportError, not a
+silent fallback.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB_PATH = os.environ.get("WARP_RNNT_LIB", os.path.join(_PKG, "lib", "libwarprnnt.so"))
+
+
+class rnntOptions(C.Structure):
+    """include/rnnt.h `struct rnntOptions` (32 bytes, by value)."""
+    _fields_ = [("loc", C.c_int), ("num_threads", C.c_uint), ("stream", C.c_void_p),
+                ("blank_label", C.c_int), ("maxT", C.c_int), ("maxU", C.c_int),
+                ("batch_first", C.c_bool)]
+
+
+RNNT_CPU, RNNT_GPU = 0, 1
+RNNT_STATUS_SUCCESS = 0
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        "libwarprnnt.so not found at %s - build it with `python warp-transducer_b200/build.py` "
+        "(there is no CPU or PyTorch fallback)" % _LIB_PATH)
+_lib = C.CDLL(_LIB_PATH)
+assert C.sizeof(rnntOptions) == 32
+
+_P = C.c_void_p
+for _name in ("compute_rnnt_loss", "compute_rnnt_loss_fp64"):
+    _f = getattr(_lib, _name)
+    _f.restype = C.c_int
+    _f.argtypes = [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, rnntOptions]
+_lib.compute_rnnt_loss_async.restype = C.c_int
+_lib.compute_rnnt_loss_async.argtypes = [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P, rnntOptions]
+_lib.compute_rnnt_loss_async_fp64.restype = C.c_int
+_lib.compute_rnnt_loss_async_fp64.argtypes = [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_double, _P, rnntOptions]
+_lib.get_workspace_size.restype = C.c_int
+_lib.get_workspace_size.argtypes = [C.c_int, C.c_int, C.c_int, C.c_bool, C.POINTER(C.c_size_t), C.c_size_t]
+_lib.get_warprnnt_version.restype = C.c_int
+_lib.rnntGetStatusString.restype = C.c_char_p
+_lib.rnntGetStatusString.argtypes = [C.c_int]
+_lib.rnnt_b200_last_launch_count.restype = C.c_int
+_lib.rnnt_b200_build_info.restype = C.c_char_p
+
+
+def lib():
+    """The loaded ctypes handle (tests and bench.py call the C-ABI through it)."""
+    return _lib
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def status_string(status):
+    return _lib.rnntGetStatusString(int(status)).decode()
+
+
+def workspace_size(maxT, maxU, minibatch, dtype_size=4, gpu=True):
+    n = C.c_size_t(0)
+    st = _lib.get_workspace_size(maxT, maxU, minibatch, gpu, C.byref(n), dtype_size)
+    if st != RNNT_STATUS_SUCCESS:
+        raise ValueError("get_workspace_size: " + status_string(st))
+    return n.value
+
+
+def last_launch_count():
+    return _lib.rnnt_b200_last_launch_count()
+
+
+def _options(acts, blank_label, num_threads=0):
+    opt = rnntOptions()
+    opt.loc = RNNT_GPU
+    opt.num_threads = num_threads
+    opt.stream = torch.cuda.current_stream(acts.device).cuda_stream
+    opt.blank_label = blank_label
+    opt.maxT = acts.size(1)
+    opt.maxU = acts.size(2)
+    opt.batch_first = True
+    return opt
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() > 0 else None
+
+
+def _labels_ptr(labels):
+    # U == 1 (no labels at all): the ABI still wants a non-null pointer
+    return labels.data_ptr() if labels.numel() > 0 else labels.new_zeros(1).data_ptr()
+
+
+def gpu_rnnt(acts, labels, input_lengths, label_lengths, costs, grads, blank_label, num_threads):
+    """Reference signature (binding.cpp:84-91).  `costs` is a CPU tensor [N] (as the reference
+    binding requires) or a CUDA tensor; `grads` is like `acts`, or empty for loss only.
+    Returns 0 on success, raises on a library error (the reference ignored the status)."""
+    if not acts.is_cuda:
+        raise RuntimeError("gpu_rnnt needs CUDA tensors")
+    N, T, U, V = acts.shape
+    if acts.dtype == torch.float32:
+        fn, esz = _lib.compute_rnnt_loss, 4
+    elif acts.dtype == torch.float64:
+        fn, esz = _lib.compute_rnnt_loss_fp64, 8
+    else:
+        raise TypeError("unsupported data type %s" % acts.dtype)
+    with torch.cuda.device(acts.device):
+        ws = torch.empty(workspace_size(T, U, N, esz), dtype=torch.uint8, device=acts.device)
+        st = fn(acts.data_ptr(), _ptr(grads), _labels_ptr(labels), label_lengths.data_ptr(),
+                input_lengths.data_ptr(), V, N, costs.data_ptr(), ws.data_ptr(),
+                _options(acts, blank_label, num_threads))
+    if st != RNNT_STATUS_SUCCESS:
+        raise RuntimeError("compute_rnnt_loss failed: " + status_string(st))
+    return 0
+
+
+def gpu_rnnt_async(acts, labels, input_lengths, label_lengths, costs, grads, blank_label,
+                   grad_scale=1.0, workspace=None):
+    """Extension: no host synchronisation, `costs` on the device, gradients pre-multiplied by
+    `grad_scale`.  Returns the workspace tensor (keep it alive until the stream has run)."""
+    N, T, U, V = acts.shape
+    if acts.dtype == torch.float32:
+        fn, esz = _lib.compute_rnnt_loss_async, 4
+    elif acts.dtype == torch.float64:
+        fn, esz = _lib.compute_rnnt_loss_async_fp64, 8
+    else:
+        raise TypeError("unsupported data type %s" % acts.dtype)
+    with torch.cuda.device(acts.device):
+        need = workspace_size(T, U, N, esz)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=acts.device)
+        st = fn(acts.data_ptr(), _ptr(grads), _labels_ptr(labels), label_lengths.data_ptr(),
+                input_lengths.data_ptr(), V, N, costs.data_ptr(), grad_scale, workspace.data_ptr(),
+                _options(acts, blank_label))
+    if st != RNNT_STATUS_SUCCESS:
+        raise RuntimeError("compute_rnnt_loss_async failed: " + status_string(st))
+    return workspace
+
+
+def cpu_rnnt(acts, labels, input_lengths, label_lengths, costs, grads, blank_label, num_threads):
+    """Reference signature (binding.cpp:12-19).  Not available: the B200 build is the device
+    path only and must not fall back to a host implementation."""
+    raise RuntimeError("warprnnt_pytorch (B200 build): cpu_rnnt is not available - "
+                       "move the tensors to a CUDA device")
