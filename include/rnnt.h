@@ -152,6 +152,13 @@ rnntStatus_t compute_rnnt_loss_async_fp64(const double* const activations, doubl
 /* Number of kernels the last compute call on this thread launched (bench.py's gpu_launches). */
 int rnnt_b200_last_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline leg.  With profiling enabled on the calling
+ * thread, each compute call records CUDA events on options.stream around its three kernels;
+ * rnnt_b200_last_kernel_ms() waits for them and writes {rowstats, lattice, grad} milliseconds
+ * (-1 where not run) and returns how many were measured. */
+void rnnt_b200_set_profiling(int enabled);
+int rnnt_b200_last_kernel_ms(float* ms3);
+
 /* Build identification string, e.g. "b200-rnnt sm_100a <date>". */
 const char* rnnt_b200_build_info(void);
 

@@ -21,7 +21,7 @@ def wr():
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"^\s*(?:rnntStatus_t|int|const char\*)\s+(\w+)\s*\(", src, flags=re.M)
+    names = re.findall(r"^\s*(?:rnntStatus_t|int|void|const char\*)\s+(\w+)\s*\(", src, flags=re.M)
     return sorted(set(names))
 
 

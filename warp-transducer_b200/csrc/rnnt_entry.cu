@@ -20,14 +20,25 @@ namespace {
 
 thread_local int g_last_launches = 0;
 
+// Optional per-kernel timing (bench.py's roofline leg): when enabled, events are recorded on the
+// call's own stream around each of the three kernels; rnnt_b200_last_kernel_ms() reads them back.
+thread_local bool g_profile = false;
+thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+thread_local bool g_ev_valid[4] = {false, false, false, false};
+inline void mark(int i, cudaStream_t s) {
+    if (!g_profile) return;
+    if (!g_ev[i]) cudaEventCreate(&g_ev[i]);
+    g_ev_valid[i] = cudaEventRecord(g_ev[i], s) == cudaSuccess;
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- workspace carve-up (all sections 256-B aligned) -------------------------------------------
 struct Workspace {
     void* stat;     // pair<T>  [rows]   (row max, log sum exp)
-    void* lp2;      // pair<T>  [rows]   (blank, label) log-probs
-    double* alphas; // [rows]
-    double* betas;  // [rows]
+    void* lp2;      // pair<T>  [lat]    (blank, label) log-probs, diagonal-major
+    double* alphas; // [lat]   lat = N*(maxT+maxU-1)*maxU
+    double* betas;  // [lat]
     double* llf;    // [N]
     double* llb;    // [N]
     void* costs;    // T [N]
@@ -37,7 +48,7 @@ struct Workspace {
     size_t bytes;
 };
 
-Workspace carve(void* base, size_t rows, int N, int maxU, size_t dtype) {
+Workspace carve(void* base, size_t rows, size_t lat, int N, int maxU, size_t dtype) {
     Workspace w;
     size_t off = align_up(reinterpret_cast<uintptr_t>(base), 256) - reinterpret_cast<uintptr_t>(base);
     char* p = static_cast<char*>(base);
@@ -47,9 +58,9 @@ Workspace carve(void* base, size_t rows, int N, int maxU, size_t dtype) {
         return q;
     };
     w.stat = take(rows * 2 * dtype);
-    w.lp2 = take(rows * 2 * dtype);
-    w.alphas = static_cast<double*>(take(rows * sizeof(double)));
-    w.betas = static_cast<double*>(take(rows * sizeof(double)));
+    w.lp2 = take(lat * 2 * dtype);
+    w.alphas = static_cast<double*>(take(lat * sizeof(double)));
+    w.betas = static_cast<double*>(take(lat * sizeof(double)));
     w.llf = static_cast<double*>(take(N * sizeof(double)));
     w.llb = static_cast<double*>(take(N * sizeof(double)));
     w.costs = take(N * dtype);
@@ -175,7 +186,8 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
     g_last_launches = 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(opt.stream);
     const int sms = device_info().sms;
-    Workspace w = carve(workspace, rows64, N, opt.maxU, sizeof(T));
+    const size_t lat = (size_t)N * (opt.maxT + opt.maxU - 1) * opt.maxU;
+    Workspace w = carve(workspace, rows64, lat, N, opt.maxU, sizeof(T));
 
     Dims d;
     d.N = N;
@@ -208,8 +220,11 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
         }
     }
 
+    for (int i = 0; i < 4; ++i) g_ev_valid[i] = false;
+    mark(0, s);
     // pass 1: log-softmax statistics + (blank, label) log-prob gather
     stream_pass<T>(acts, nullptr, labels, xlen, ylen, w, scale, d, s, sms, 1);
+    mark(1, s);
 
     // lattice: alpha (and beta when gradients are wanted), one CTA per (utterance, direction)
     {
@@ -226,9 +241,13 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
                 w.llf, w.llb, cdev, d);
         ++g_last_launches;
     }
+    mark(2, s);
 
     // pass 2: dense gradient (+ zeros on padding)
-    if (grads) stream_pass<T>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, 2);
+    if (grads) {
+        stream_pass<T>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, 2);
+        mark(3, s);
+    }
 
     if (cudaGetLastError() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
     if (async) return RNNT_STATUS_SUCCESS;
@@ -308,7 +327,8 @@ rnntStatus_t get_workspace_size(int maxT, int maxU, int minibatch, bool gpu, siz
         *size_bytes = dtype_size * rows * 4;
         return RNNT_STATUS_SUCCESS;
     }
-    *size_bytes = carve(nullptr, rows, minibatch, maxU, dtype_size).bytes;
+    const size_t lat = (size_t)minibatch * (maxT + maxU - 1) * maxU;
+    *size_bytes = carve(nullptr, rows, lat, minibatch, maxU, dtype_size).bytes;
     return RNNT_STATUS_SUCCESS;
 }
 
@@ -318,6 +338,20 @@ rnntStatus_t get_rnnt_workspace_size(int maxT, int maxU, int minibatch, bool gpu
 }
 
 int rnnt_b200_last_launch_count(void) { return g_last_launches; }
+
+void rnnt_b200_set_profiling(int enabled) { g_profile = enabled != 0; }
+
+int rnnt_b200_last_kernel_ms(float* ms3) {
+    if (!ms3) return 0;
+    int n = 0;
+    for (int i = 0; i < 3; ++i) {
+        ms3[i] = -1.0f;
+        if (g_ev_valid[i] && g_ev_valid[i + 1] && cudaEventSynchronize(g_ev[i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms3[i], g_ev[i], g_ev[i + 1]) == cudaSuccess)
+            ++n;
+    }
+    return n;
+}
 
 const char* rnnt_b200_build_info(void) { return "b200-rnnt sm_100a built " __DATE__ " " __TIME__; }
 

@@ -24,6 +24,17 @@ struct Dims {
     FastDiv divU, divT;
 };
 
+// The lattice arrays (lp2, alphas, betas) are stored DIAGONAL-MAJOR per utterance: cell (t,u)
+// lives at (t+u)*maxU + u inside a block of (maxT+maxU-1)*maxU entries.  The wavefront kernel
+// touches one anti-diagonal per step, so its loads and stores are contiguous across the u-threads
+// (one or two 128-B lines per warp instead of 32 scattered sectors in the row-major form).
+__host__ __device__ __forceinline__ size_t lattice_block(const Dims& d) {
+    return (size_t)(d.maxT + d.maxU - 1) * d.maxU;
+}
+__device__ __forceinline__ size_t skew(const Dims& d, uint32_t b, uint32_t t, uint32_t u) {
+    return (size_t)b * lattice_block(d) + (size_t)(t + u) * d.maxU + u;
+}
+
 // clamp the per-utterance extents into the tensor so corrupt lengths cannot index outside it
 __device__ __forceinline__ void utt_extent(const Dims& d, const int* __restrict__ xlen,
                                            const int* __restrict__ ylen, int b, int& T, int& U) {
@@ -111,7 +122,7 @@ rowstats_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
                 const int y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
                 lp.y = (__ldg(row + y) - M) - lse;
             }
-            lp2[r] = lp;
+            lp2[skew(d, b, t, u)] = lp;
         }
     }
 }
@@ -141,8 +152,8 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
     const int nwarps = blockDim.x >> 5;
     int Tb, Ub;
     utt_extent(d, xlen, ylen, b, Tb, Ub);
-    const size_t base = (size_t)b * d.maxT * d.maxU;
-    const typename Real<T>::pair* lp = lp2 + base;
+    const size_t base = (size_t)b * lattice_block(d);
+    const typename Real<T>::pair* lp = lp2 + base;  // diagonal-major: lp[n*maxU + u] = cell (n-u, u)
     const int last = Tb + Ub - 2;
     const bool mine = u < Ub;
     const int mU = d.maxU;
@@ -158,8 +169,8 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
             s_ = 0;
             e_ = 0;
             if (mine && n <= last && t >= 0 && t < Tb) {
-                if (t > 0) s_ = __ldg(&lp[(size_t)(t - 1) * mU + u].x);
-                if (u > 0) e_ = __ldg(&lp[(size_t)t * mU + u - 1].y);
+                if (t > 0) s_ = __ldg(&lp[(size_t)(n - 1) * mU + u].x);      // cell (t-1, u)
+                if (u > 0) e_ = __ldg(&lp[(size_t)(n - 1) * mU + u - 1].y);  // cell (t, u-1)
             }
         };
 #pragma unroll
@@ -180,14 +191,14 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
                         const double stay = t > 0 ? a + (double)sx[j] : NINF;
                         const double emit = u > 0 ? a_left + (double)ey[j] : NINF;
                         a = lse_step<T>(stay, emit);
-                        al[(size_t)t * mU + u] = a;
+                        al[(size_t)n * mU + u] = a;
                     }
                     fetch(n + PF, sx[j], ey[j]);
                 }
             }
         }
         if (u == Ub - 1) {
-            const double ll = a + (double)__ldg(&lp[(size_t)(Tb - 1) * mU + Ub - 1].x);
+            const double ll = a + (double)__ldg(&lp[(size_t)last * mU + Ub - 1].x);
             llf[b] = ll;
             costs[b] = (T)(-ll);
         }
@@ -201,7 +212,7 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
             x_ = 0;
             y_ = 0;
             if (mine && n >= 0 && t >= 0 && t < Tb) {
-                const typename Real<T>::pair p = __ldg(&lp[(size_t)t * mU + u]);
+                const typename Real<T>::pair p = __ldg(&lp[(size_t)n * mU + u]);
                 x_ = p.x;
                 y_ = p.y;
             }
@@ -228,7 +239,7 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
                             const double emit = u < Ub - 1 ? b_right + (double)py[j] : NINF;
                             bv = lse_step<T>(stay, emit);
                         }
-                        be[(size_t)t * mU + u] = bv;
+                        be[(size_t)n * mU + u] = bv;
                     }
                     fetch(n - PF, px[j], py[j]);
                 }
@@ -283,19 +294,20 @@ grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __rest
             continue;
         }
         const typename R::pair st = __ldg(stat + r);
-        const double a = alphas[r];
+        const size_t q = skew(d, b, t, u);  // (t+1,u) is at q + maxU, (t,u+1) at q + maxU + 1
+        const double a = alphas[q];
         const double occ = a - __ldg(llf + b);
         const T m = st.x;
         // offsets in the exp2 domain: 2^{(x-m)*log2e + c}
-        const T cA = ((T)(occ + betas[r]) - st.y) * R::kLog2e;
+        const T cA = ((T)(occ + betas[q]) - st.y) * R::kLog2e;
         T cB = R::neg_inf(), cL = R::neg_inf();
         if ((int)t < Tb - 1)
-            cB = ((T)(occ + betas[r + d.maxU]) - st.y) * R::kLog2e;
+            cB = ((T)(occ + betas[q + d.maxU]) - st.y) * R::kLog2e;
         else if ((int)u == Ub - 1)
             cB = ((T)occ - st.y) * R::kLog2e;
         int y = -1;
         if ((int)u < Ub - 1) {
-            cL = ((T)(occ + betas[r + 1]) - st.y) * R::kLog2e;
+            cL = ((T)(occ + betas[q + d.maxU + 1]) - st.y) * R::kLog2e;
             y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
         }
         const int kb = d.blank;

@@ -49,6 +49,10 @@ _lib.rnntGetStatusString.restype = C.c_char_p
 _lib.rnntGetStatusString.argtypes = [C.c_int]
 _lib.rnnt_b200_last_launch_count.restype = C.c_int
 _lib.rnnt_b200_build_info.restype = C.c_char_p
+_lib.rnnt_b200_set_profiling.restype = None
+_lib.rnnt_b200_set_profiling.argtypes = [C.c_int]
+_lib.rnnt_b200_last_kernel_ms.restype = C.c_int
+_lib.rnnt_b200_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
 
 
 def lib():
@@ -74,6 +78,17 @@ def workspace_size(maxT, maxU, minibatch, dtype_size=4, gpu=True):
 
 def last_launch_count():
     return _lib.rnnt_b200_last_launch_count()
+
+
+def set_profiling(enabled):
+    _lib.rnnt_b200_set_profiling(1 if enabled else 0)
+
+
+def last_kernel_ms():
+    """(rowstats, lattice, grad) milliseconds of the last profiled call on this thread."""
+    out = (C.c_float * 3)()
+    _lib.rnnt_b200_last_kernel_ms(out)
+    return tuple(out)
 
 
 def _options(acts, blank_label, num_threads=0):
