@@ -30,6 +30,8 @@ def main():
         ws = None
         for mode, g in (("loss+grad", grads), ("loss", None)):
             ts = []
+            wr.set_profiling(True)
+            km = np.zeros(3)
             for it in range(8):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -38,12 +40,14 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
+                if it >= 3:
+                    km += np.array(wr.last_kernel_ms()) / 5
             t = float(np.median(ts[3:]))
             E = N * T * U * V
             bytes_ = (12 if g is not None else 4) * E
-            print("%s %-9s N=%d T=%d U=%d V=%d: %.3f ms  %.0f utt/s  %.0f GB/s (algorithmic %d B/elt)  cost[0]=%.3f" % (
+            print("%s %-9s N=%d T=%d U=%d V=%d: %.3f ms  %.0f utt/s  %.0f GB/s (algorithmic %d B/elt)  cost[0]=%.3f  kernels(rowstats,lattice,grad)=%s" % (
                 name, mode, N, T, U, V, t, N / t * 1e3, bytes_ / t / 1e6, 12 if g is not None else 4,
-                costs[0].item()), flush=True)
+                costs[0].item(), np.round(km, 3)), flush=True)
         del acts, grads
         torch.cuda.empty_cache()
 

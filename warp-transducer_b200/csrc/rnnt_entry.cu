@@ -7,6 +7,7 @@
 // No memset pass, no intermediate host synchronisation.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_runtime.h>
@@ -131,20 +132,68 @@ void launch_grad(const T* acts, T* grads, const int* labels, const int* xlen, co
     ++g_last_launches;
 }
 
+template <typename T, int VEC, int LPR>
+void launch_rowstats_tile(const T* acts, const int* labels, const int* xlen, const int* ylen,
+                          const Workspace& w, const Dims& d, cudaStream_t s, int sms) {
+    auto k = rowstats_tile_kernel<T, VEC, LPR>;
+    static thread_local int blocks = 0;
+    if (!blocks) blocks = blocks_for(k, 256, sms);
+    const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;
+    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks);
+    k<<<grid, 256, 0, s>>>(acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
+                           static_cast<typename Real<T>::pair*>(w.lp2), d);
+    ++g_last_launches;
+}
+
+template <typename T, int VEC, int LPR>
+void launch_grad_tile(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+                      const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms) {
+    auto k = grad_tile_kernel<T, VEC, LPR>;
+    static thread_local int blocks = 0;
+    if (!blocks) blocks = blocks_for(k, 256, sms);
+    const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;
+    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks);
+    k<<<grid, 256, 0, s>>>(acts, grads, labels, xlen, ylen,
+                           static_cast<const typename Real<T>::pair*>(w.stat), w.alphas, w.betas,
+                           w.llf, scale, d);
+    ++g_last_launches;
+}
+
+// lanes per row for the register-tile kernels: aim at ~4 vectors per lane (<= kVPL = 8)
+inline int pick_lpr(int nv) {
+    static const int forced = [] {
+        const char* e = getenv("RNNT_B200_LPR");  // tuning hook
+        return e ? atoi(e) : 0;
+    }();
+    int lpr = 1;
+    while (lpr < 32 && lpr * 4 < nv) lpr *= 2;
+    if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0 && forced * kVPL >= nv) lpr = forced;
+    return lpr;
+}
+
 template <typename T, int VEC>
 void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
                    const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms, int pass) {
     const int nv = d.V / VEC;
-    if (nv <= 8) {
-        if (pass == 1) launch_rowstats<T, VEC, 8, 1>(acts, labels, xlen, ylen, w, d, s, sms);
-        else launch_grad<T, VEC, 8, 1>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
-    } else if (nv <= 64) {
-        if (pass == 1) launch_rowstats<T, VEC, 32, 1>(acts, labels, xlen, ylen, w, d, s, sms);
-        else launch_grad<T, VEC, 32, 1>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
-    } else {
+    if (nv > 32 * kVPL) {  // long rows: one row per warp, looped, online statistics
         if (pass == 1) launch_rowstats<T, VEC, 32, 4>(acts, labels, xlen, ylen, w, d, s, sms);
         else launch_grad<T, VEC, 32, 4>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+        return;
     }
+#define B200_TILE(L)                                                                              \
+    case L:                                                                                       \
+        if (pass == 1) launch_rowstats_tile<T, VEC, L>(acts, labels, xlen, ylen, w, d, s, sms);   \
+        else launch_grad_tile<T, VEC, L>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);   \
+        break;
+    switch (pick_lpr(nv)) {
+        B200_TILE(1)
+        B200_TILE(2)
+        B200_TILE(4)
+        B200_TILE(8)
+        B200_TILE(16)
+        B200_TILE(32)
+    }
+#undef B200_TILE
 }
 
 template <typename T>
@@ -231,14 +280,18 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
         const int threads = (opt.maxU + 31) / 32 * 32;
         dim3 grid(N, grads ? 2 : 1);
         T* cdev = async ? costs : static_cast<T*>(w.costs);
-        if (threads > 32)
-            lattice_kernel<T, true><<<grid, threads, 0, s>>>(
-                static_cast<const typename Real<T>::pair*>(w.lp2), xlen, ylen, w.alphas, w.betas,
-                w.llf, w.llb, cdev, d);
-        else
-            lattice_kernel<T, false><<<grid, threads, 0, s>>>(
-                static_cast<const typename Real<T>::pair*>(w.lp2), xlen, ylen, w.alphas, w.betas,
-                w.llf, w.llb, cdev, d);
+        const size_t ring = (size_t)kRing * threads * sizeof(typename Real<T>::pair);
+        auto launch = [&](auto kernel) {
+            static thread_local size_t opted = 0;
+            if (ring > 48 * 1024 && ring > opted) {
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+                opted = ring;
+            }
+            kernel<<<grid, threads, ring, s>>>(static_cast<const typename Real<T>::pair*>(w.lp2), xlen,
+                                              ylen, w.alphas, w.betas, w.llf, w.llb, cdev, d);
+        };
+        if (threads > 32) launch(lattice_kernel<T, true>);
+        else launch(lattice_kernel<T, false>);
         ++g_last_launches;
     }
     mark(2, s);

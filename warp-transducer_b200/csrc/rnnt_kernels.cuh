@@ -128,121 +128,216 @@ rowstats_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
 }
 
 // =================================================================================================
+// Pass 1, short rows (V/VEC <= 8*LPR): the whole row lives in registers — each of the LPR lanes
+// of a row holds up to kVPL vectors, all loads are issued before the first use (32*kVPL*16 B in
+// flight per warp whatever V is), and the statistics are the exact two-pass max / sum exp(x-max).
+// Small LPR keeps the per-row bookkeeping (index decode, length checks, lattice stores) off most
+// lanes: at V=28 two lanes own a row, at V=50 (float2) four do.
+// =================================================================================================
+constexpr int kVPL = 8;
+
+template <typename T, int VEC, int LPR>
+__global__ void __launch_bounds__(256)
+rowstats_tile_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
+                     const int* __restrict__ xlen, const int* __restrict__ ylen,
+                     typename Real<T>::pair* __restrict__ stat,
+                     typename Real<T>::pair* __restrict__ lp2, const Dims d) {
+    using R = Real<T>;
+    constexpr int RPW = kWarp / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = d.V / VEC;
+
+    for (uint64_t r0 = (uint64_t)gw * RPW; r0 < d.rows; r0 += (uint64_t)warps_total * RPW) {
+        const uint32_t r = (uint32_t)r0 + sub;
+        bool valid = r < d.rows;
+        uint32_t bt = 0, u = 0, b = 0, t = 0;
+        int Tb = 0, Ub = 0;
+        if (valid) {
+            d.divU.divmod(r, bt, u);
+            d.divT.divmod(bt, b, t);
+            utt_extent(d, xlen, ylen, b, Tb, Ub);
+            valid = (int)t < Tb && (int)u < Ub;
+        }
+        const T* row = acts + (uint64_t)r * d.V;
+        VecT<T, VEC> x[kVPL];
+#pragma unroll
+        for (int j = 0; j < kVPL; ++j) {
+            const int i = sl + j * LPR;
+            if (valid && i < nv) {
+                x[j] = ld_keep<T, VEC>(row + (size_t)i * VEC);
+            } else {
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) x[j].v[c] = R::neg_inf();
+            }
+        }
+        T m = x[0].v[0];
+#pragma unroll
+        for (int j = 0; j < kVPL; ++j)
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) m = x[j].v[c] > m ? x[j].v[c] : m;
+        const T M = group_max<LPR>(m);
+        const T Mz = (M == R::neg_inf()) ? T(0) : M;
+        T s = 0;
+#pragma unroll
+        for (int j = 0; j < kVPL; ++j)
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) s += R::exp(x[j].v[c] - Mz);
+        const T S = group_sum<LPR>(s);
+        if (valid && sl == 0) {
+            const T lse = R::log(S);
+            typename R::pair st;
+            st.x = M;
+            st.y = lse;
+            stat[r] = st;
+            typename R::pair lp;
+            lp.x = (__ldg(row + d.blank) - M) - lse;
+            lp.y = 0;
+            if ((int)u < Ub - 1) {
+                const int y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+                lp.y = (__ldg(row + y) - M) - lse;
+            }
+            lp2[skew(d, b, t, u)] = lp;
+        }
+    }
+}
+
+// =================================================================================================
 // Lattice DP.  grid = (N, 2): blockIdx.y 0 -> alpha (forward), 1 -> beta (backward); the two
 // directions of an utterance run concurrently on different SMs.  One thread per u; anti-diagonal
-// n = t + u is the step index, so thread u handles cell (n - u, u) at step n.  The u-1 (u+1)
-// neighbour's value comes by warp shuffle; across warps through a double-buffered shared slot
-// and ONE __syncthreads per diagonal (none when maxU <= 32).  The (blank,label) log-probs of the
-// next PF diagonals are prefetched into registers, so the dependent chain per step is
-//   shuffle -> DADD -> max/min -> ex2 -> lg2 -> DADD.
-// alpha/beta are carried and stored in double (see lse_step).
+// n = t + u is the step index, so thread u handles cell (n - u, u) at step n.
+//
+//  * The (blank,label) log-prob pairs of the next kRing-2 diagonals are in flight as cp.async
+//    copies into a shared-memory ring (the lattice is diagonal-major, so a diagonal is one
+//    contiguous run).  cp.async completion is counted in order (wait_group), unlike register
+//    prefetches whose scoreboard slots alias and collapse the prefetch distance to one step.
+//  * The u-1 (u+1) neighbour's running value comes by warp shuffle; across warps through a
+//    double-buffered shared slot and ONE __syncthreads per diagonal (a __syncwarp when maxU <= 32).
+//  * Boundary cells need no branches: a column starts from -inf (alpha) so "stay" vanishes at
+//    t = 0, the emit log-prob is forced to -inf at u = 0 (alpha) / u = U-1 (beta), and beta's
+//    virtual cell beta(T, U-1) = 0 makes the terminal cell fall out of the same recurrence.
+//  * alpha/beta are carried and stored in double; the dependent chain per step is
+//    SHFL -> DADD -> DADD -> F2F -> FMNMX/FMUL -> MUFU.EX2 -> FADD -> MUFU.LG2 -> FMUL -> F2F -> DADD.
 // =================================================================================================
+constexpr int kRing = 8;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// log(e^x + e^y) for the lattice: doubles in/out, correction term in the caller's precision.
+template <typename T> __device__ __forceinline__ double lse2(double x, double y) {
+    if (sizeof(T) == 4) {
+        const float df = (float)(x - y);          // +-inf when one side is -inf, NaN when both are
+        const double mx = df > 0.0f ? x : y;
+        // min(.,0) turns the NaN of (-inf)-(-inf) into 0: the result is then y + ln2 = -inf
+        const float nd = fminf(-fabsf(df), 0.0f) * 1.4426950408889634f;
+        float e, l;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(nd));
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+        return mx + (double)(l * 0.6931471805599453f);
+    } else {
+        const double mx = fmax(x, y), mn = fmin(x, y);
+        if (mx == -(double)INFINITY) return mx;
+        return mx + log1p(::exp(mn - mx));
+    }
+}
+
 template <typename T, bool MULTI>
 __global__ void __launch_bounds__(1024)
 lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __restrict__ xlen,
                const int* __restrict__ ylen, double* __restrict__ alphas,
                double* __restrict__ betas, double* __restrict__ llf, double* __restrict__ llb,
                T* __restrict__ costs, const Dims d) {
-    constexpr int PF = 4;
+    using P = typename Real<T>::pair;
     constexpr double NINF = -(double)INFINITY;
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    P* ring = reinterpret_cast<P*>(ring_raw);  // [kRing][blockDim.x]
     __shared__ double edge[2][32];
     const int b = blockIdx.x;
     const int u = threadIdx.x;
+    const int NT = blockDim.x;
     const int lane = u & 31, warp = u >> 5;
-    const int nwarps = blockDim.x >> 5;
+    const int nwarps = NT >> 5;
     int Tb, Ub;
     utt_extent(d, xlen, ylen, b, Tb, Ub);
     const size_t base = (size_t)b * lattice_block(d);
-    const typename Real<T>::pair* lp = lp2 + base;  // diagonal-major: lp[n*maxU + u] = cell (n-u, u)
     const int last = Tb + Ub - 2;
     const bool mine = u < Ub;
     const int mU = d.maxU;
+    const P* lp_u = lp2 + base + u;  // diagonal-major: lp_u[n*mU] = cell (n-u, u)
+
+    // copy this thread's cell of diagonal dg into the ring (no-op outside the lattice); the commit
+    // is unconditional so every thread's group count advances in lock step with the step index
+    auto issue = [&](int dg) {
+        const int t = dg - u;
+        if (mine && dg >= 0 && dg <= last && t >= 0 && t < Tb)
+            cp_async<sizeof(P)>(&ring[(dg & (kRing - 1)) * NT + u], lp_u + (size_t)dg * mU);
+        cp_async_commit();
+    };
 
     if (blockIdx.y == 0) {
         // ------------------------------------------------------------------ alpha
-        double* al = alphas + base;
+        double* al_u = alphas + base + u;
         double a = (u == 0) ? 0.0 : NINF;  // alpha(t-1, u) of this thread's column
-        if (u == 0) al[0] = 0.0;
-        T sx[PF], ey[PF];
-        auto fetch = [&](int n, T& s_, T& e_) {
-            const int t = n - u;
-            s_ = 0;
-            e_ = 0;
-            if (mine && n <= last && t >= 0 && t < Tb) {
-                if (t > 0) s_ = __ldg(&lp[(size_t)(n - 1) * mU + u].x);      // cell (t-1, u)
-                if (u > 0) e_ = __ldg(&lp[(size_t)(n - 1) * mU + u - 1].y);  // cell (t, u-1)
+        if (u == 0) al_u[0] = 0.0;
+#pragma unroll
+        for (int k = 0; k < kRing - 1; ++k) issue(k);
+        for (int n = 1; n <= last; ++n) {
+            cp_async_wait<kRing - 2>();  // diagonal n-1 has landed (this thread's part)
+            if (MULTI) {
+                if (lane == 31) edge[n & 1][warp] = a;
+                __syncthreads();
+            } else {
+                __syncwarp();
             }
-        };
-#pragma unroll
-        for (int j = 0; j < PF; ++j) fetch(1 + j, sx[j], ey[j]);
-        for (int n0 = 1; n0 <= last; n0 += PF) {
-#pragma unroll
-            for (int j = 0; j < PF; ++j) {
-                const int n = n0 + j;
-                if (n <= last) {  // block-uniform
-                    if (MULTI) {
-                        if (lane == 31) edge[n & 1][warp] = a;
-                        __syncthreads();
-                    }
-                    double a_left = __shfl_up_sync(0xffffffffu, a, 1);
-                    if (MULTI && lane == 0) a_left = warp > 0 ? edge[n & 1][warp - 1] : NINF;
-                    const int t = n - u;
-                    if (mine && t >= 0 && t < Tb) {
-                        const double stay = t > 0 ? a + (double)sx[j] : NINF;
-                        const double emit = u > 0 ? a_left + (double)ey[j] : NINF;
-                        a = lse_step<T>(stay, emit);
-                        al[(size_t)n * mU + u] = a;
-                    }
-                    fetch(n + PF, sx[j], ey[j]);
-                }
+            issue(n + kRing - 2);  // reuses the slot of diagonal n-2, which nobody reads any more
+            double a_left = __shfl_up_sync(0xffffffffu, a, 1);
+            if (MULTI && lane == 0 && warp > 0) a_left = edge[n & 1][warp - 1];
+            const int t = n - u;
+            if (mine && t >= 0 && t < Tb) {
+                const P* slot = ring + ((n - 1) & (kRing - 1)) * NT + u;
+                const T sx = t > 0 ? slot[0].x : T(0);                   // lp_blank(t-1, u)
+                const T ey = u > 0 ? slot[-1].y : Real<T>::neg_inf();    // lp_label(t, u-1)
+                a = lse2<T>(a + (double)sx, a_left + (double)ey);
+                al_u[(size_t)n * mU] = a;
             }
         }
         if (u == Ub - 1) {
-            const double ll = a + (double)__ldg(&lp[(size_t)last * mU + Ub - 1].x);
+            cp_async_wait<0>();
+            const double ll = a + (double)lp_u[(size_t)last * mU].x;
             llf[b] = ll;
             costs[b] = (T)(-ll);
         }
     } else {
         // ------------------------------------------------------------------ beta
-        double* be = betas + base;
-        double bv = NINF;  // beta(t+1, u) of this thread's column
-        T px[PF], py[PF];
-        auto fetch = [&](int n, T& x_, T& y_) {
-            const int t = n - u;
-            x_ = 0;
-            y_ = 0;
-            if (mine && n >= 0 && t >= 0 && t < Tb) {
-                const typename Real<T>::pair p = __ldg(&lp[(size_t)n * mU + u]);
-                x_ = p.x;
-                y_ = p.y;
+        double* be_u = betas + base + u;
+        double bv = (u == Ub - 1) ? 0.0 : NINF;  // beta(t+1, u); virtual beta(T, U-1) = 0
+#pragma unroll
+        for (int k = 0; k < kRing - 1; ++k) issue(last - k);
+        for (int n = last; n >= 0; --n) {
+            cp_async_wait<kRing - 2>();  // this thread's cell of diagonal n has landed
+            if (MULTI) {
+                if (lane == 0) edge[n & 1][warp] = bv;
+                __syncthreads();
             }
-        };
-#pragma unroll
-        for (int j = 0; j < PF; ++j) fetch(last - j, px[j], py[j]);
-        for (int n0 = last; n0 >= 0; n0 -= PF) {
-#pragma unroll
-            for (int j = 0; j < PF; ++j) {
-                const int n = n0 - j;
-                if (n >= 0) {  // block-uniform
-                    if (MULTI) {
-                        if (lane == 0) edge[n & 1][warp] = bv;
-                        __syncthreads();
-                    }
-                    double b_right = __shfl_down_sync(0xffffffffu, bv, 1);
-                    if (MULTI && lane == 31) b_right = warp + 1 < nwarps ? edge[n & 1][warp + 1] : NINF;
-                    const int t = n - u;
-                    if (mine && t >= 0 && t < Tb) {
-                        if (t == Tb - 1 && u == Ub - 1) {
-                            bv = (double)px[j];
-                        } else {
-                            const double stay = t < Tb - 1 ? bv + (double)px[j] : NINF;
-                            const double emit = u < Ub - 1 ? b_right + (double)py[j] : NINF;
-                            bv = lse_step<T>(stay, emit);
-                        }
-                        be[(size_t)n * mU + u] = bv;
-                    }
-                    fetch(n - PF, px[j], py[j]);
-                }
+            issue(n - (kRing - 1));  // slot of diagonal n+1: written and read by this thread only
+            double b_right = __shfl_down_sync(0xffffffffu, bv, 1);
+            if (MULTI && lane == 31 && warp + 1 < nwarps) b_right = edge[n & 1][warp + 1];
+            const int t = n - u;
+            if (mine && t >= 0 && t < Tb) {
+                const P p = ring[(n & (kRing - 1)) * NT + u];
+                const T py = u < Ub - 1 ? p.y : Real<T>::neg_inf();
+                bv = lse2<T>(bv + (double)p.x, b_right + (double)py);
+                be_u[(size_t)n * mU] = bv;
             }
         }
         if (u == 0) llb[b] = bv;
@@ -335,6 +430,107 @@ grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __rest
                     }
                     st_stream<T, VEC>(grow + (size_t)i * VEC, g);
                 }
+            }
+        }
+    }
+}
+
+
+// Per-row constants of the gradient: offsets in the exp2 domain (see grad_kernel).
+template <typename T> struct RowGrad {
+    T m, cA, cB, cL;
+    int y;
+};
+template <typename T>
+__device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, uint32_t b, uint32_t t,
+                                                     uint32_t u, int Tb, int Ub,
+                                                     const int* __restrict__ labels,
+                                                     const typename Real<T>::pair* __restrict__ stat,
+                                                     const double* __restrict__ alphas,
+                                                     const double* __restrict__ betas,
+                                                     const double* __restrict__ llf) {
+    using R = Real<T>;
+    RowGrad<T> g;
+    const typename R::pair st = __ldg(stat + r);
+    const size_t q = skew(d, b, t, u);  // (t+1,u) is at q + maxU, (t,u+1) at q + maxU + 1
+    const double occ = alphas[q] - __ldg(llf + b);
+    g.m = st.x;
+    g.cA = ((T)(occ + betas[q]) - st.y) * R::kLog2e;
+    g.cB = R::neg_inf();
+    g.cL = R::neg_inf();
+    if ((int)t < Tb - 1)
+        g.cB = ((T)(occ + betas[q + d.maxU]) - st.y) * R::kLog2e;
+    else if ((int)u == Ub - 1)
+        g.cB = ((T)occ - st.y) * R::kLog2e;
+    g.y = -1;
+    if ((int)u < Ub - 1) {
+        g.cL = ((T)(occ + betas[q + d.maxU + 1]) - st.y) * R::kLog2e;
+        g.y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+    }
+    return g;
+}
+
+// Pass 2, short rows: same register tile as rowstats_tile_kernel.
+template <typename T, int VEC, int LPR>
+__global__ void __launch_bounds__(256)
+grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
+                 const int* __restrict__ xlen, const int* __restrict__ ylen,
+                 const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
+                 const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
+                 const Dims d) {
+    using R = Real<T>;
+    constexpr int RPW = kWarp / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = d.V / VEC;
+    const int kb = d.blank;
+
+    for (uint64_t r0 = (uint64_t)gw * RPW; r0 < d.rows; r0 += (uint64_t)warps_total * RPW) {
+        const uint64_t rr = r0 + sub;
+        if (rr >= d.rows) continue;
+        const uint32_t r = d.rows - 1 - (uint32_t)rr;
+        uint32_t bt, u, b, t;
+        d.divU.divmod(r, bt, u);
+        d.divT.divmod(bt, b, t);
+        int Tb, Ub;
+        utt_extent(d, xlen, ylen, b, Tb, Ub);
+        const T* row = acts + (uint64_t)r * d.V;
+        T* grow = grads + (uint64_t)r * d.V;
+        if ((int)t >= Tb || (int)u >= Ub) {
+            VecT<T, VEC> z;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) z.v[c] = 0;
+#pragma unroll
+            for (int j = 0; j < kVPL; ++j) {
+                const int i = sl + j * LPR;
+                if (i < nv) st_stream<T, VEC>(grow + (size_t)i * VEC, z);
+            }
+            continue;
+        }
+        VecT<T, VEC> x[kVPL];
+#pragma unroll
+        for (int j = 0; j < kVPL; ++j) {
+            const int i = sl + j * LPR;
+            if (i < nv) x[j] = ld_stream<T, VEC>(row + (size_t)i * VEC);
+        }
+        const RowGrad<T> rg = row_grad_setup<T>(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
+#pragma unroll
+        for (int j = 0; j < kVPL; ++j) {
+            const int i = sl + j * LPR;
+            if (i < nv) {
+                const int k0 = i * VEC;
+                VecT<T, VEC> g;
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) {
+                    const T dl = (x[j].v[c] - rg.m) * R::kLog2e;
+                    T gv = R::exp2(dl + rg.cA);
+                    if (k0 + c == kb) gv -= R::exp2(dl + rg.cB);
+                    if (k0 + c == rg.y) gv -= R::exp2(dl + rg.cL);
+                    g.v[c] = gv * scale;
+                }
+                st_stream<T, VEC>(grow + (size_t)i * VEC, g);
             }
         }
     }
