@@ -118,14 +118,15 @@ void launch_rowstats(const T* acts, const int* labels, const int* xlen, const in
     ++g_last_launches;
 }
 
-template <typename T, int VEC, int LPR, int UNR>
+template <typename T, int VEC, int UNR>
 void launch_grad(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
                  const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms) {
-    auto k = grad_kernel<T, VEC, LPR, UNR>;
-    static thread_local int blocks = 0;
-    if (!blocks) blocks = blocks_for(k, 256, sms);
-    const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;
-    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks);
+    const bool scaled = scale != T(1);
+    auto k = scaled ? grad_kernel<T, VEC, UNR, true> : grad_kernel<T, VEC, UNR, false>;
+    static thread_local int blocks[2] = {0, 0};
+    if (!blocks[scaled]) blocks[scaled] = blocks_for(k, 256, sms);
+    const uint64_t row_groups = d.rows;
+    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks[scaled]);
     k<<<grid, 256, 0, s>>>(acts, grads, labels, xlen, ylen,
                            static_cast<const typename Real<T>::pair*>(w.stat), w.alphas, w.betas,
                            w.llf, scale, d);
@@ -148,25 +149,27 @@ void launch_rowstats_tile(const T* acts, const int* labels, const int* xlen, con
 template <typename T, int VEC, int LPR>
 void launch_grad_tile(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
                       const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms) {
-    auto k = grad_tile_kernel<T, VEC, LPR>;
-    static thread_local int blocks = 0;
-    if (!blocks) blocks = blocks_for(k, 256, sms);
+    const bool scaled = scale != T(1);
+    auto k = scaled ? grad_tile_kernel<T, VEC, LPR, true> : grad_tile_kernel<T, VEC, LPR, false>;
+    static thread_local int blocks[2] = {0, 0};
+    if (!blocks[scaled]) blocks[scaled] = blocks_for(k, 256, sms);
     const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;
-    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks);
+    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks[scaled]);
     k<<<grid, 256, 0, s>>>(acts, grads, labels, xlen, ylen,
                            static_cast<const typename Real<T>::pair*>(w.stat), w.alphas, w.betas,
                            w.llf, scale, d);
     ++g_last_launches;
 }
 
-// lanes per row for the register-tile kernels: aim at ~4 vectors per lane (<= kVPL = 8)
+// lanes per row for the register-tile kernels: the fewest lanes (>= 2) whose kVPL = 8 vector
+// registers hold the row - measured on B200: V=28 -> 2 lanes, V=50 (float2) -> 4 lanes per row
 inline int pick_lpr(int nv) {
     static const int forced = [] {
         const char* e = getenv("RNNT_B200_LPR");  // tuning hook
         return e ? atoi(e) : 0;
     }();
-    int lpr = 1;
-    while (lpr < 32 && lpr * 4 < nv) lpr *= 2;
+    int lpr = 2;
+    while (lpr < 32 && lpr * kVPL < nv) lpr *= 2;
     if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0 && forced * kVPL >= nv) lpr = forced;
     return lpr;
 }
@@ -177,7 +180,15 @@ void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, 
     const int nv = d.V / VEC;
     if (nv > 32 * kVPL) {  // long rows: one row per warp, looped, online statistics
         if (pass == 1) launch_rowstats<T, VEC, 32, 4>(acts, labels, xlen, ylen, w, d, s, sms);
-        else launch_grad<T, VEC, 32, 4>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+        else {
+            static const int unr = [] {
+                const char* e = getenv("RNNT_B200_GRAD_UNR");  // tuning hook: 2, 4 (default) or 8
+                return e ? atoi(e) : 4;
+            }();
+            if (unr == 2) launch_grad<T, VEC, 2>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+            else if (unr == 8) launch_grad<T, VEC, 8>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+            else launch_grad<T, VEC, 4>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+        }
         return;
     }
 #define B200_TILE(L)                                                                              \

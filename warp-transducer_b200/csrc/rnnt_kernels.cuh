@@ -345,102 +345,49 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
 }
 
 // =================================================================================================
-// Pass 2: dense gradient w.r.t. the logits, same row->lane mapping as pass 1, rows visited in
-// reverse so the tail of pass 1 is met first in L2.
+// Pass 2: dense gradient w.r.t. the logits, rows visited in reverse so the tail of pass 1 is met
+// first in L2.
 //   g_k = scale * ( e^{lp_k + alpha + beta - ll}
-//                   - [k = blank, t < T-1]        e^{lp_k + alpha + beta(t+1,u) - ll}
+//                   - [k = blank, t < T-1]          e^{lp_k + alpha + beta(t+1,u) - ll}
 //                   - [k = blank, t = T-1, u = U-1] e^{lp_k + alpha - ll}
-//                   - [k = y_u,  u < U-1]         e^{lp_k + alpha + beta(t,u+1) - ll} )
+//                   - [k = y_u,  u < U-1]           e^{lp_k + alpha + beta(t,u+1) - ll} )
 // (reference gpu_rnnt_kernel.h:159-177), lp_k = (x_k - m) - lse.  The three per-row offsets are
-// formed once per row in double and rounded; per element the work is FADD, FFMA, MUFU.EX2, FMUL.
-// Padded rows are written as zeros here (no separate memset pass).
+// formed once per row in double and rounded (exp2 domain); per element the work is
+// FADD (x-m), FFMA, MUFU.EX2 (+ FMUL when scale != 1).  The two special lanes (blank, label)
+// are patched per VECTOR, not per element.  Padded rows are written as zeros here (no memset pass).
 // =================================================================================================
-template <typename T, int VEC, int LPR, int UNR>
-__global__ void __launch_bounds__(256)
-grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
-            const int* __restrict__ xlen, const int* __restrict__ ylen,
-            const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
-            const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
-            const Dims d) {
-    using R = Real<T>;
-    constexpr int RPW = kWarp / LPR;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LPR, sl = lane % LPR;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int nv = d.V / VEC;
-
-    for (uint64_t r0 = (uint64_t)gw * RPW; r0 < d.rows; r0 += (uint64_t)warps_total * RPW) {
-        const uint64_t rr = r0 + sub;
-        if (rr >= d.rows) continue;
-        const uint32_t r = d.rows - 1 - (uint32_t)rr;
-        uint32_t bt, u, b, t;
-        d.divU.divmod(r, bt, u);
-        d.divT.divmod(bt, b, t);
-        int Tb, Ub;
-        utt_extent(d, xlen, ylen, b, Tb, Ub);
-        const T* row = acts + (uint64_t)r * d.V;
-        T* grow = grads + (uint64_t)r * d.V;
-        if ((int)t >= Tb || (int)u >= Ub) {
-            VecT<T, VEC> z;
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) z.v[c] = 0;
-            for (int i = sl; i < nv; i += LPR) st_stream<T, VEC>(grow + (size_t)i * VEC, z);
-            continue;
-        }
-        const typename R::pair st = __ldg(stat + r);
-        const size_t q = skew(d, b, t, u);  // (t+1,u) is at q + maxU, (t,u+1) at q + maxU + 1
-        const double a = alphas[q];
-        const double occ = a - __ldg(llf + b);
-        const T m = st.x;
-        // offsets in the exp2 domain: 2^{(x-m)*log2e + c}
-        const T cA = ((T)(occ + betas[q]) - st.y) * R::kLog2e;
-        T cB = R::neg_inf(), cL = R::neg_inf();
-        if ((int)t < Tb - 1)
-            cB = ((T)(occ + betas[q + d.maxU]) - st.y) * R::kLog2e;
-        else if ((int)u == Ub - 1)
-            cB = ((T)occ - st.y) * R::kLog2e;
-        int y = -1;
-        if ((int)u < Ub - 1) {
-            cL = ((T)(occ + betas[q + d.maxU + 1]) - st.y) * R::kLog2e;
-            y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
-        }
-        const int kb = d.blank;
-
-        for (int i0 = sl; i0 < nv; i0 += LPR * UNR) {
-            VecT<T, VEC> x[UNR];
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-                const int i = i0 + j * LPR;
-                if (i < nv) x[j] = ld_stream<T, VEC>(row + (size_t)i * VEC);
-            }
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-                const int i = i0 + j * LPR;
-                if (i < nv) {
-                    const int k0 = i * VEC;
-                    VecT<T, VEC> g;
-#pragma unroll
-                    for (int c = 0; c < VEC; ++c) {
-                        const T dl = (x[j].v[c] - m) * R::kLog2e;
-                        T gv = R::exp2(dl + cA);
-                        if (k0 + c == kb) gv -= R::exp2(dl + cB);
-                        if (k0 + c == y) gv -= R::exp2(dl + cL);
-                        g.v[c] = gv * scale;
-                    }
-                    st_stream<T, VEC>(grow + (size_t)i * VEC, g);
-                }
-            }
-        }
-    }
-}
-
-
 // Per-row constants of the gradient: offsets in the exp2 domain (see grad_kernel).
 template <typename T> struct RowGrad {
     T m, cA, cB, cL;
     int y;
 };
+
+// one vector of gradient from one vector of logits; k0 = index of its first element
+template <typename T, int VEC, bool SCALED>
+__device__ __forceinline__ VecT<T, VEC> grad_vec(const VecT<T, VEC>& x, const RowGrad<T>& rg, int k0,
+                                                 int kb, T scale) {
+    using R = Real<T>;
+    VecT<T, VEC> g;
+    T dl[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+        dl[c] = x.v[c] - rg.m;
+        g.v[c] = R::exp2(fma(dl[c], (T)R::kLog2e, rg.cA));
+    }
+    // blank / label lanes: at most two vectors of the row take this branch
+    if ((unsigned)(kb - k0) < (unsigned)VEC || (unsigned)(rg.y - k0) < (unsigned)VEC) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            if (k0 + c == kb) g.v[c] -= R::exp2(fma(dl[c], (T)R::kLog2e, rg.cB));
+            if (k0 + c == rg.y) g.v[c] -= R::exp2(fma(dl[c], (T)R::kLog2e, rg.cL));
+        }
+    }
+    if (SCALED) {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) g.v[c] *= scale;
+    }
+    return g;
+}
 template <typename T>
 __device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, uint32_t b, uint32_t t,
                                                      uint32_t u, int Tb, int Ub,
@@ -455,7 +402,7 @@ __device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, 
     const size_t q = skew(d, b, t, u);  // (t+1,u) is at q + maxU, (t,u+1) at q + maxU + 1
     const double occ = alphas[q] - __ldg(llf + b);
     g.m = st.x;
-    g.cA = ((T)(occ + betas[q]) - st.y) * R::kLog2e;
+    g.cA = ((T)(occ + betas[q]) - st.y) * (T)R::kLog2e;
     g.cB = R::neg_inf();
     g.cL = R::neg_inf();
     if ((int)t < Tb - 1)
@@ -470,15 +417,76 @@ __device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, 
     return g;
 }
 
+
+// Pass 2, long rows: one row per warp, UNR 16-B vectors per lane per trip, software-pipelined —
+// the next trip's loads (and the row's lattice constants) are in flight while the current trip is
+// exponentiated and stored.
+template <typename T, int VEC, int UNR, bool SCALED>
+__global__ void __launch_bounds__(256)
+grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
+            const int* __restrict__ xlen, const int* __restrict__ ylen,
+            const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
+            const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
+            const Dims d) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = d.V / VEC;
+    const int kb = d.blank;
+    constexpr int STEP = kWarp * UNR;
+
+    for (uint64_t rr = gw; rr < d.rows; rr += warps_total) {
+        const uint32_t r = d.rows - 1 - (uint32_t)rr;
+        uint32_t bt, u, b, t;
+        d.divU.divmod(r, bt, u);
+        d.divT.divmod(bt, b, t);
+        int Tb, Ub;
+        utt_extent(d, xlen, ylen, b, Tb, Ub);
+        const T* row = acts + (uint64_t)r * d.V;
+        T* grow = grads + (uint64_t)r * d.V;
+        if ((int)t >= Tb || (int)u >= Ub) {
+            VecT<T, VEC> z;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) z.v[c] = 0;
+            for (int i = lane; i < nv; i += kWarp) st_stream<T, VEC>(grow + (size_t)i * VEC, z);
+            continue;
+        }
+        VecT<T, VEC> xa[UNR], xb[UNR];
+        auto load = [&](VecT<T, VEC>(&x)[UNR], int i0) {
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int i = i0 + j * kWarp;
+                if (i < nv) x[j] = ld_stream<T, VEC>(row + (size_t)i * VEC);
+            }
+        };
+        load(xa, lane);  // first trip is in flight before the lattice constants are fetched
+        const RowGrad<T> rg = row_grad_setup<T>(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
+        auto emit = [&](const VecT<T, VEC>(&x)[UNR], int i0) {
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int i = i0 + j * kWarp;
+                if (i < nv)
+                    st_stream<T, VEC>(grow + (size_t)i * VEC,
+                                      grad_vec<T, VEC, SCALED>(x[j], rg, i * VEC, kb, scale));
+            }
+        };
+        for (int i0 = lane; i0 < nv; i0 += 2 * STEP) {
+            load(xb, i0 + STEP);
+            emit(xa, i0);
+            load(xa, i0 + 2 * STEP);
+            emit(xb, i0 + STEP);
+        }
+    }
+}
+
 // Pass 2, short rows: same register tile as rowstats_tile_kernel.
-template <typename T, int VEC, int LPR>
+template <typename T, int VEC, int LPR, bool SCALED>
 __global__ void __launch_bounds__(256)
 grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
                  const int* __restrict__ xlen, const int* __restrict__ ylen,
                  const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
                  const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
                  const Dims d) {
-    using R = Real<T>;
     constexpr int RPW = kWarp / LPR;
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPR, sl = lane % LPR;
@@ -519,19 +527,9 @@ grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* _
 #pragma unroll
         for (int j = 0; j < kVPL; ++j) {
             const int i = sl + j * LPR;
-            if (i < nv) {
-                const int k0 = i * VEC;
-                VecT<T, VEC> g;
-#pragma unroll
-                for (int c = 0; c < VEC; ++c) {
-                    const T dl = (x[j].v[c] - rg.m) * R::kLog2e;
-                    T gv = R::exp2(dl + rg.cA);
-                    if (k0 + c == kb) gv -= R::exp2(dl + rg.cB);
-                    if (k0 + c == rg.y) gv -= R::exp2(dl + rg.cL);
-                    g.v[c] = gv * scale;
-                }
-                st_stream<T, VEC>(grow + (size_t)i * VEC, g);
-            }
+            if (i < nv)
+                st_stream<T, VEC>(grow + (size_t)i * VEC,
+                                  grad_vec<T, VEC, SCALED>(x[j], rg, i * VEC, kb, scale));
         }
     }
 }
