@@ -123,6 +123,10 @@ void launch_grad(const T* acts, T* grads, const int* labels, const int* xlen, co
                  const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms) {
     const bool scaled = scale != T(1);
     auto k = scaled ? grad_kernel<T, VEC, UNR, true> : grad_kernel<T, VEC, UNR, false>;
+    static const int pol = [] { const char* e = getenv("RNNT_B200_POL"); return e ? atoi(e) : 0; }();
+    if (!scaled && UNR == 4 && pol == 1) k = grad_kernel<T, VEC, UNR, false, 1>;
+    if (!scaled && UNR == 4 && pol == 2) k = grad_kernel<T, VEC, UNR, false, 2>;
+    if (!scaled && UNR == 4 && pol == 3) k = grad_kernel<T, VEC, UNR, false, 3>;
     static thread_local int blocks[2] = {0, 0};
     if (!blocks[scaled]) blocks[scaled] = blocks_for(k, 256, sms);
     const uint64_t row_groups = d.rows;

@@ -421,7 +421,7 @@ __device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, 
 // Pass 2, long rows: one row per warp, UNR 16-B vectors per lane per trip, software-pipelined —
 // the next trip's loads (and the row's lattice constants) are in flight while the current trip is
 // exponentiated and stored.
-template <typename T, int VEC, int UNR, bool SCALED>
+template <typename T, int VEC, int UNR, bool SCALED, int POL = 0>
 __global__ void __launch_bounds__(256)
 grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
             const int* __restrict__ xlen, const int* __restrict__ ylen,
@@ -456,7 +456,7 @@ grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __rest
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
                 const int i = i0 + j * kWarp;
-                if (i < nv) x[j] = ld_stream<T, VEC>(row + (size_t)i * VEC);
+                if (i < nv) x[j] = (POL & 1) ? ld_keep<T, VEC>(row + (size_t)i * VEC) : ld_stream<T, VEC>(row + (size_t)i * VEC);
             }
         };
         load(xa, lane);  // first trip is in flight before the lattice constants are fetched
@@ -465,9 +465,11 @@ grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __rest
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
                 const int i = i0 + j * kWarp;
-                if (i < nv)
-                    st_stream<T, VEC>(grow + (size_t)i * VEC,
-                                      grad_vec<T, VEC, SCALED>(x[j], rg, i * VEC, kb, scale));
+                if (i < nv) {
+                    const VecT<T, VEC> g = grad_vec<T, VEC, SCALED>(x[j], rg, i * VEC, kb, scale);
+                    if (POL & 2) *reinterpret_cast<VecT<T, VEC>*>(grow + (size_t)i * VEC) = g;
+                    else st_stream<T, VEC>(grow + (size_t)i * VEC, g);
+                }
             }
         };
         for (int i0 = lane; i0 < nv; i0 += 2 * STEP) {
