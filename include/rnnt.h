@@ -158,6 +158,10 @@ int rnnt_b200_last_launch_count(void);
  * (-1 where not run) and returns how many were measured. */
 void rnnt_b200_set_profiling(int enabled);
 int rnnt_b200_last_kernel_ms(float* ms3);
+/* Mean {rowstats, lattice, grad} milliseconds over every call recorded on this thread since the
+ * previous collect (waits for their events), returns the number of calls and resets the record.
+ * Lets a timed loop run without any host synchronisation between steps. */
+int rnnt_b200_profile_collect(float* ms3_mean);
 
 /* Build identification string, e.g. "b200-rnnt sm_100a <date>". */
 const char* rnnt_b200_build_info(void);

@@ -158,7 +158,12 @@ SHAPES = [
     (3, 6, 3, 257, 0),     # scalar, > 64 -> unrolled path
     (2, 4, 3, 1000, 7),    # float4 unrolled
     (2, 3, 2, 5000, 0),    # README large vocab rows
-    (2, 5, 3, 5002, 0),    # float2 unrolled
+    (2, 5, 3, 5002, 0),    # float2, CTA per row
+    (2, 4, 3, 514, 0),     # float2, 257 vectors: CTA per row, 2 per thread
+    (2, 4, 3, 1028, 5),    # float4, 257 vectors
+    (1, 3, 2, 8200, 0),    # float4, 2050 vectors: two trips of the CTA-per-row loop
+    (1, 2, 2, 33001, 7),   # scalar rows, 17 trips
+    (2, 3, 2, 301, 0),     # scalar, 2 per thread, partial second slot
     (4, 20, 33, 6, 0),     # U > 32: multi-warp lattice
     (2, 9, 70, 4, 0),      # 3 warps
     (3, 40, 1, 6, 0),      # U == 1: empty label sequences

@@ -1,0 +1,162 @@
+// Bandwidth probe (dev tool): what limits the read+write pass?  Variants of an 8 GB -> 8 GB stream.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <vector>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
+
+__global__ void copy_gridstride(const float4* __restrict__ in, float4* __restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = in[i];
+}
+// one block of 256 threads copies 4 float4 per thread, non-persistent (torch-like)
+__global__ void copy_flat(const float4* __restrict__ in, float4* __restrict__ out, size_t n) {
+    size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (base + j * 256 < n) v[j] = __ldcs(in + base + j * 256);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (base + j * 256 < n) __stcs(out + base + j * 256, v[j]);
+}
+template <int MATH, int UNR>
+__global__ void __launch_bounds__(256) rows_warp(const float* __restrict__ in, float* __restrict__ out, int rows, int V) {
+    const int lane = threadIdx.x & 31;
+    const unsigned wt = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = V / 4;
+    for (unsigned rr = gw; rr < (unsigned)rows; rr += wt) {
+        const unsigned r = rows - 1 - rr;
+        const float4* row = reinterpret_cast<const float4*>(in + (size_t)r * V);
+        float4* orow = reinterpret_cast<float4*>(out + (size_t)r * V);
+        for (int i0 = lane; i0 < nv; i0 += 32 * UNR) {
+            float4 x[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) if (i0 + j * 32 < nv) x[j] = __ldcs(row + i0 + j * 32);
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) if (i0 + j * 32 < nv) {
+                float4 g = x[j];
+                if (MATH) { g.x = exp2f(g.x * 1.44f - 3.f); g.y = exp2f(g.y * 1.44f - 3.f); g.z = exp2f(g.z * 1.44f - 3.f); g.w = exp2f(g.w * 1.44f - 3.f); }
+                __stcs(orow + i0 + j * 32, g);
+            }
+        }
+    }
+}
+// CTA-per-chunk: block b handles a contiguous chunk of 64 KB repeatedly (block-linear moving window)
+template <int MATH>
+__global__ void __launch_bounds__(256) chunk_window(const float4* __restrict__ in, float4* __restrict__ out, size_t n) {
+    const size_t per_iter = (size_t)gridDim.x * 1024;
+    for (size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x; base < n; base += per_iter) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (base + j * 256 < n) v[j] = __ldcs(in + base + j * 256);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (base + j * 256 < n) {
+            float4 g = v[j];
+            if (MATH) { g.x = exp2f(g.x * 1.44f - 3.f); g.y = exp2f(g.y * 1.44f - 3.f); g.z = exp2f(g.z * 1.44f - 3.f); g.w = exp2f(g.w * 1.44f - 3.f); }
+            __stcs(out + base + j * 256, g);
+        }
+    }
+}
+
+// CTA per row, non-persistent: thread i owns vectors i, i+256, ... (<= NV per thread), all loads first
+template <int MATH, int NV>
+__global__ void __launch_bounds__(256) row_cta(const float* __restrict__ in, float* __restrict__ out, int rows, int V) {
+    const unsigned r = rows - 1 - blockIdx.x;
+    const int nv = V / 4;
+    const float4* row = reinterpret_cast<const float4*>(in + (size_t)r * V);
+    float4* orow = reinterpret_cast<float4*>(out + (size_t)r * V);
+    float4 x[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) if (threadIdx.x + j * 256 < nv) x[j] = __ldcs(row + threadIdx.x + j * 256);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) if (threadIdx.x + j * 256 < nv) {
+        float4 g = x[j];
+        if (MATH) { g.x = exp2f(g.x * 1.44f - 3.f); g.y = exp2f(g.y * 1.44f - 3.f); g.z = exp2f(g.z * 1.44f - 3.f); g.w = exp2f(g.w * 1.44f - 3.f); }
+        __stcs(orow + threadIdx.x + j * 256, g);
+    }
+}
+// read-only probes: sum into a sink so the loads stay
+__global__ void read_flat(const float4* __restrict__ in, float* sink, size_t n) {
+    size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    float acc = 0;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (base + j * 256 < n) v[j] = __ldg(in + base + j * 256); else v[j] = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc += v[j].x + v[j].y + v[j].z + v[j].w;
+    if (acc == 123.456f) *sink = acc;
+}
+template <int NV>
+__global__ void __launch_bounds__(256) read_row_cta(const float* __restrict__ in, float* sink, int rows, int V) {
+    const unsigned r = blockIdx.x;
+    const int nv = V / 4;
+    const float4* row = reinterpret_cast<const float4*>(in + (size_t)r * V);
+    float4 x[NV];
+    float acc = 0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) if (threadIdx.x + j * 256 < nv) x[j] = __ldg(row + threadIdx.x + j * 256); else x[j] = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc += x[j].x + x[j].y + x[j].z + x[j].w;
+    if (acc == 123.456f) *sink = acc;
+}
+template <int UNR>
+__global__ void __launch_bounds__(256) read_rows_warp(const float* __restrict__ in, float* sink, int rows, int V) {
+    const int lane = threadIdx.x & 31;
+    const unsigned wt = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = V / 4;
+    float acc = 0;
+    for (unsigned r = gw; r < (unsigned)rows; r += wt) {
+        const float4* row = reinterpret_cast<const float4*>(in + (size_t)r * V);
+        for (int i0 = lane; i0 < nv; i0 += 32 * UNR) {
+            float4 x[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) if (i0 + j * 32 < nv) x[j] = __ldg(row + i0 + j * 32); else x[j] = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) acc += x[j].x + x[j].y + x[j].z + x[j].w;
+        }
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
+int main() {
+    const int rows = 128 * 150 * 21, V = 5000;
+    const size_t n = (size_t)rows * V, n4 = n / 4;
+    float *a, *b;
+    CK(cudaMalloc(&a, n * 4)); CK(cudaMalloc(&b, n * 4));
+    CK(cudaMemset(a, 0, n * 4));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    auto time = [&](const char* name, auto launch) {
+        float best = 1e9, sum = 0;
+        for (int it = 0; it < 8; ++it) {
+            cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (it >= 2) { best = ms < best ? ms : best; sum += ms; }
+        }
+        printf("%-44s best %.3f ms  mean %.3f ms  -> %.0f GB/s (r+w)\n", name, best, sum / 6, 2.0 * n * 4 / (sum / 6) / 1e6);
+        return 0;
+    };
+    time("cudaMemcpy D2D", [&] { cudaMemcpyAsync(b, a, n * 4, cudaMemcpyDeviceToDevice); });
+    time("copy_flat (non-persistent, 4xfloat4/thread)", [&] { copy_flat<<<(unsigned)((n4 + 1023) / 1024), 256>>>((float4*)a, (float4*)b, n4); });
+    for (int occ : {4, 8}) { char nm[64]; snprintf(nm, 64, "copy_gridstride %d blk/SM", occ);
+        time(nm, [&] { copy_gridstride<<<sms * occ, 256>>>((float4*)a, (float4*)b, n4); }); }
+    for (int occ : {3, 5, 8}) { char nm[64];
+        snprintf(nm, 64, "rows_warp copy UNR4 %d blk/SM", occ); time(nm, [&] { rows_warp<0, 4><<<sms * occ, 256>>>(a, b, rows, V); });
+        snprintf(nm, 64, "rows_warp exp  UNR4 %d blk/SM", occ); time(nm, [&] { rows_warp<1, 4><<<sms * occ, 256>>>(a, b, rows, V); });
+        snprintf(nm, 64, "rows_warp copy UNR8 %d blk/SM", occ); time(nm, [&] { rows_warp<0, 8><<<sms * occ, 256>>>(a, b, rows, V); });
+    }
+    for (int occ : {4, 8}) { char nm[64];
+        snprintf(nm, 64, "chunk_window copy %d blk/SM", occ); time(nm, [&] { chunk_window<0><<<sms * occ, 256>>>((float4*)a, (float4*)b, n4); });
+        snprintf(nm, 64, "chunk_window exp  %d blk/SM", occ); time(nm, [&] { chunk_window<1><<<sms * occ, 256>>>((float4*)a, (float4*)b, n4); });
+    }
+    time("row_cta copy (CTA per row, non-persistent)", [&] { row_cta<0, 5><<<rows, 256>>>(a, b, rows, V); });
+    time("row_cta exp  (CTA per row, non-persistent)", [&] { row_cta<1, 5><<<rows, 256>>>(a, b, rows, V); });
+    time("rows_warp copy UNR4 non-persistent 8 rows/CTA", [&] { rows_warp<0, 4><<<rows / 8, 256>>>(a, b, rows, V); });
+    time("rows_warp exp  UNR4 non-persistent 8 rows/CTA", [&] { rows_warp<1, 4><<<rows / 8, 256>>>(a, b, rows, V); });
+    time("rows_warp copy UNR8 non-persistent 8 rows/CTA", [&] { rows_warp<0, 8><<<rows / 8, 256>>>(a, b, rows, V); });
+    printf("read-only probes: GB/s printed below is DOUBLE the true read rate\n");
+    time("read_flat non-persistent", [&] { read_flat<<<(unsigned)((n4 + 1023) / 1024), 256>>>((float4*)a, b, n4); });
+    time("read_row_cta non-persistent", [&] { read_row_cta<5><<<rows, 256>>>(a, b, rows, V); });
+    time("read_rows_warp UNR4 persistent 6 blk/SM", [&] { read_rows_warp<4><<<sms * 6, 256>>>(a, b, rows, V); });
+    time("read_rows_warp UNR4 non-persistent", [&] { read_rows_warp<4><<<rows / 8, 256>>>(a, b, rows, V); });
+    return 0;
+}

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -22,14 +23,37 @@ namespace {
 thread_local int g_last_launches = 0;
 
 // Optional per-kernel timing (bench.py's roofline leg): when enabled, events are recorded on the
-// call's own stream around each of the three kernels; rnnt_b200_last_kernel_ms() reads them back.
+// call's own stream around each of the three kernels, one event set per call (pooled), so a timed
+// loop needs no host synchronisation; rnnt_b200_profile_collect() averages them afterwards.
+struct EventSet {
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool valid[4] = {false, false, false, false};
+};
 thread_local bool g_profile = false;
-thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-thread_local bool g_ev_valid[4] = {false, false, false, false};
-inline void mark(int i, cudaStream_t s) {
+thread_local std::vector<EventSet> g_sets;
+thread_local size_t g_used = 0;   // sets recorded since the last collect
+inline void profile_begin_call() {
     if (!g_profile) return;
-    if (!g_ev[i]) cudaEventCreate(&g_ev[i]);
-    g_ev_valid[i] = cudaEventRecord(g_ev[i], s) == cudaSuccess;
+    if (g_used == g_sets.size()) g_sets.emplace_back();
+    EventSet& es = g_sets[g_used++];
+    for (int i = 0; i < 4; ++i) es.valid[i] = false;
+}
+inline void mark(int i, cudaStream_t s) {
+    if (!g_profile || g_used == 0) return;
+    EventSet& es = g_sets[g_used - 1];
+    if (!es.e[i]) cudaEventCreate(&es.e[i]);
+    es.valid[i] = cudaEventRecord(es.e[i], s) == cudaSuccess;
+}
+// ms of {rowstats, lattice, grad} for one recorded call; false where not measured
+inline int read_set(EventSet& es, float* ms3) {
+    int n = 0;
+    for (int i = 0; i < 3; ++i) {
+        ms3[i] = -1.0f;
+        if (es.valid[i] && es.valid[i + 1] && cudaEventSynchronize(es.e[i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms3[i], es.e[i], es.e[i + 1]) == cudaSuccess)
+            ++n;
+    }
+    return n;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -96,72 +120,47 @@ bool is_device_pointer(const void* p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-template <typename K> int blocks_for(K kernel, int threads, int sms) {
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
-    if (per_sm < 1) per_sm = 1;
-    return per_sm * sms;
-}
 
-// ---- streaming-kernel dispatch on (vector width, lanes per row) ---------------------------------
-template <typename T, int VEC, int LPR, int UNR>
-void launch_rowstats(const T* acts, const int* labels, const int* xlen, const int* ylen,
-                     const Workspace& w, const Dims& d, cudaStream_t s, int sms) {
-    auto k = rowstats_kernel<T, VEC, LPR, UNR>;
-    static thread_local int blocks = 0;
-    if (!blocks) blocks = blocks_for(k, 256, sms);
-    const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;  // warps of work
-    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks);
-    k<<<grid, 256, 0, s>>>(acts, labels, xlen, ylen,
-                           static_cast<typename Real<T>::pair*>(w.stat),
-                           static_cast<typename Real<T>::pair*>(w.lp2), d);
+// ---- streaming-kernel dispatch on (vector width, row length) -------------------------------------
+// Long rows: one CTA per row (grid = rows).  Short rows: register tiles, 32/LPR rows per warp.
+// Both grids are non-persistent on purpose (see rnnt_kernels.cuh).
+template <typename T, int VEC, int NV>
+void launch_rowstats_row(const T* acts, const int* labels, const int* xlen, const int* ylen,
+                         const Workspace& w, const Dims& d, cudaStream_t s) {
+    rowstats_row_kernel<T, VEC, NV><<<d.rows, kRowThreads, 0, s>>>(
+        acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
+        static_cast<typename Real<T>::pair*>(w.lp2), d);
     ++g_last_launches;
 }
 
-template <typename T, int VEC, int UNR>
-void launch_grad(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
-                 const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms) {
-    const bool scaled = scale != T(1);
-    auto k = scaled ? grad_kernel<T, VEC, UNR, true> : grad_kernel<T, VEC, UNR, false>;
-    static const int pol = [] { const char* e = getenv("RNNT_B200_POL"); return e ? atoi(e) : 0; }();
-    if (!scaled && UNR == 4 && pol == 1) k = grad_kernel<T, VEC, UNR, false, 1>;
-    if (!scaled && UNR == 4 && pol == 2) k = grad_kernel<T, VEC, UNR, false, 2>;
-    if (!scaled && UNR == 4 && pol == 3) k = grad_kernel<T, VEC, UNR, false, 3>;
-    static thread_local int blocks[2] = {0, 0};
-    if (!blocks[scaled]) blocks[scaled] = blocks_for(k, 256, sms);
-    const uint64_t row_groups = d.rows;
-    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks[scaled]);
-    k<<<grid, 256, 0, s>>>(acts, grads, labels, xlen, ylen,
-                           static_cast<const typename Real<T>::pair*>(w.stat), w.alphas, w.betas,
-                           w.llf, scale, d);
+template <typename T, int VEC, int NV>
+void launch_grad_row(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+                     const Workspace& w, T scale, const Dims& d, cudaStream_t s) {
+    auto k = scale != T(1) ? grad_row_kernel<T, VEC, NV, true> : grad_row_kernel<T, VEC, NV, false>;
+    k<<<d.rows, kRowThreads, 0, s>>>(acts, grads, labels, xlen, ylen,
+                                      static_cast<const typename Real<T>::pair*>(w.stat), w.alphas,
+                                      w.betas, w.llf, scale, d);
     ++g_last_launches;
 }
 
 template <typename T, int VEC, int LPR>
 void launch_rowstats_tile(const T* acts, const int* labels, const int* xlen, const int* ylen,
-                          const Workspace& w, const Dims& d, cudaStream_t s, int sms) {
-    auto k = rowstats_tile_kernel<T, VEC, LPR>;
-    static thread_local int blocks = 0;
-    if (!blocks) blocks = blocks_for(k, 256, sms);
-    const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;
-    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks);
-    k<<<grid, 256, 0, s>>>(acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
-                           static_cast<typename Real<T>::pair*>(w.lp2), d);
+                          const Workspace& w, const Dims& d, cudaStream_t s) {
+    const uint64_t warps = ((uint64_t)d.rows * LPR + 31) / 32;
+    rowstats_tile_kernel<T, VEC, LPR><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(
+        acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
+        static_cast<typename Real<T>::pair*>(w.lp2), d);
     ++g_last_launches;
 }
 
 template <typename T, int VEC, int LPR>
 void launch_grad_tile(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
-                      const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms) {
-    const bool scaled = scale != T(1);
-    auto k = scaled ? grad_tile_kernel<T, VEC, LPR, true> : grad_tile_kernel<T, VEC, LPR, false>;
-    static thread_local int blocks[2] = {0, 0};
-    if (!blocks[scaled]) blocks[scaled] = blocks_for(k, 256, sms);
-    const uint64_t row_groups = ((uint64_t)d.rows * LPR + 31) / 32;
-    int grid = (int)std::min<uint64_t>((row_groups + 7) / 8, (uint64_t)blocks[scaled]);
-    k<<<grid, 256, 0, s>>>(acts, grads, labels, xlen, ylen,
-                           static_cast<const typename Real<T>::pair*>(w.stat), w.alphas, w.betas,
-                           w.llf, scale, d);
+                      const Workspace& w, T scale, const Dims& d, cudaStream_t s) {
+    auto k = scale != T(1) ? grad_tile_kernel<T, VEC, LPR, true> : grad_tile_kernel<T, VEC, LPR, false>;
+    const uint64_t warps = ((uint64_t)d.rows * LPR + 31) / 32;
+    k<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(acts, grads, labels, xlen, ylen,
+                                                  static_cast<const typename Real<T>::pair*>(w.stat),
+                                                  w.alphas, w.betas, w.llf, scale, d);
     ++g_last_launches;
 }
 
@@ -180,28 +179,39 @@ inline int pick_lpr(int nv) {
 
 template <typename T, int VEC>
 void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
-                   const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms, int pass) {
+                   const Workspace& w, T scale, const Dims& d, cudaStream_t s, int pass) {
     const int nv = d.V / VEC;
-    if (nv > 32 * kVPL) {  // long rows: one row per warp, looped, online statistics
-        if (pass == 1) launch_rowstats<T, VEC, 32, 4>(acts, labels, xlen, ylen, w, d, s, sms);
-        else {
-            static const int unr = [] {
-                const char* e = getenv("RNNT_B200_GRAD_UNR");  // tuning hook: 2, 4 (default) or 8
-                return e ? atoi(e) : 4;
-            }();
-            if (unr == 2) launch_grad<T, VEC, 2>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
-            else if (unr == 8) launch_grad<T, VEC, 8>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
-            else launch_grad<T, VEC, 4>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);
+    if (nv > 32 * kVPL) {  // long rows: CTA per row; NV = vectors per thread per trip
+        const int per_thread = (nv + kRowThreads - 1) / kRowThreads;
+#define B200_ROW(NVV)                                                                             \
+    do {                                                                                          \
+        if (pass == 1) launch_rowstats_row<T, VEC, NVV>(acts, labels, xlen, ylen, w, d, s);       \
+        else launch_grad_row<T, VEC, NVV>(acts, grads, labels, xlen, ylen, w, scale, d, s);       \
+    } while (0)
+        if (sizeof(T) == 4 && VEC == 4) {  // the fp32 fast path gets an exact register count
+            switch (per_thread) {
+                case 1: B200_ROW(1); break;
+                case 2: B200_ROW(2); break;
+                case 3: B200_ROW(3); break;
+                case 4: B200_ROW(4); break;
+                case 5: B200_ROW(5); break;
+                case 6: B200_ROW(6); break;
+                default: B200_ROW(8); break;
+            }
+        } else {
+            if (per_thread <= 2) B200_ROW(2);
+            else if (per_thread <= 4) B200_ROW(4);
+            else B200_ROW(8);
         }
+#undef B200_ROW
         return;
     }
 #define B200_TILE(L)                                                                              \
     case L:                                                                                       \
-        if (pass == 1) launch_rowstats_tile<T, VEC, L>(acts, labels, xlen, ylen, w, d, s, sms);   \
-        else launch_grad_tile<T, VEC, L>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms);   \
+        if (pass == 1) launch_rowstats_tile<T, VEC, L>(acts, labels, xlen, ylen, w, d, s);        \
+        else launch_grad_tile<T, VEC, L>(acts, grads, labels, xlen, ylen, w, scale, d, s);        \
         break;
     switch (pick_lpr(nv)) {
-        B200_TILE(1)
         B200_TILE(2)
         B200_TILE(4)
         B200_TILE(8)
@@ -213,17 +223,17 @@ void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, 
 
 template <typename T>
 void stream_pass(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
-                 const Workspace& w, T scale, const Dims& d, cudaStream_t s, int sms, int pass) {
+                 const Workspace& w, T scale, const Dims& d, cudaStream_t s, int pass) {
     // widest vector the row pitch and the base pointers allow
     const uintptr_t mis = reinterpret_cast<uintptr_t>(acts) | reinterpret_cast<uintptr_t>(grads) |
                           ((uintptr_t)d.V * sizeof(T));
     constexpr int kMaxVec = 16 / sizeof(T);
     if (mis % 16 == 0)
-        stream_passes<T, kMaxVec>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, pass);
+        stream_passes<T, kMaxVec>(acts, grads, labels, xlen, ylen, w, scale, d, s, pass);
     else if (sizeof(T) == 4 && mis % 8 == 0)
-        stream_passes<T, (kMaxVec > 2 ? 2 : 1)>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, pass);
+        stream_passes<T, (kMaxVec > 2 ? 2 : 1)>(acts, grads, labels, xlen, ylen, w, scale, d, s, pass);
     else
-        stream_passes<T, 1>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, pass);
+        stream_passes<T, 1>(acts, grads, labels, xlen, ylen, w, scale, d, s, pass);
 }
 
 // ---- the path -----------------------------------------------------------------------------------
@@ -249,7 +259,6 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
 
     g_last_launches = 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(opt.stream);
-    const int sms = device_info().sms;
     const size_t lat = (size_t)N * (opt.maxT + opt.maxU - 1) * opt.maxU;
     Workspace w = carve(workspace, rows64, lat, N, opt.maxU, sizeof(T));
 
@@ -284,10 +293,10 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
         }
     }
 
-    for (int i = 0; i < 4; ++i) g_ev_valid[i] = false;
+    profile_begin_call();
     mark(0, s);
     // pass 1: log-softmax statistics + (blank, label) log-prob gather
-    stream_pass<T>(acts, nullptr, labels, xlen, ylen, w, scale, d, s, sms, 1);
+    stream_pass<T>(acts, nullptr, labels, xlen, ylen, w, scale, d, s, 1);
     mark(1, s);
 
     // lattice: alpha (and beta when gradients are wanted), one CTA per (utterance, direction)
@@ -313,7 +322,7 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
 
     // pass 2: dense gradient (+ zeros on padding)
     if (grads) {
-        stream_pass<T>(acts, grads, labels, xlen, ylen, w, scale, d, s, sms, 2);
+        stream_pass<T>(acts, grads, labels, xlen, ylen, w, scale, d, s, 2);
         mark(3, s);
     }
 
@@ -410,15 +419,27 @@ int rnnt_b200_last_launch_count(void) { return g_last_launches; }
 void rnnt_b200_set_profiling(int enabled) { g_profile = enabled != 0; }
 
 int rnnt_b200_last_kernel_ms(float* ms3) {
-    if (!ms3) return 0;
-    int n = 0;
-    for (int i = 0; i < 3; ++i) {
-        ms3[i] = -1.0f;
-        if (g_ev_valid[i] && g_ev_valid[i + 1] && cudaEventSynchronize(g_ev[i + 1]) == cudaSuccess &&
-            cudaEventElapsedTime(&ms3[i], g_ev[i], g_ev[i + 1]) == cudaSuccess)
-            ++n;
+    if (!ms3 || g_used == 0) return 0;
+    return read_set(g_sets[g_used - 1], ms3);
+}
+
+int rnnt_b200_profile_collect(float* ms3_mean) {
+    if (!ms3_mean) return 0;
+    double acc[3] = {0, 0, 0};
+    int cnt[3] = {0, 0, 0};
+    for (size_t k = 0; k < g_used; ++k) {
+        float ms[3];
+        read_set(g_sets[k], ms);
+        for (int i = 0; i < 3; ++i)
+            if (ms[i] >= 0) {
+                acc[i] += ms[i];
+                ++cnt[i];
+            }
     }
-    return n;
+    for (int i = 0; i < 3; ++i) ms3_mean[i] = cnt[i] ? (float)(acc[i] / cnt[i]) : -1.0f;
+    const int calls = (int)g_used;
+    g_used = 0;
+    return calls;
 }
 
 const char* rnnt_b200_build_info(void) { return "b200-rnnt sm_100a built " __DATE__ " " __TIME__; }

@@ -43,73 +43,78 @@ __device__ __forceinline__ void utt_extent(const Dims& d, const int* __restrict_
 }
 
 // =================================================================================================
-// Pass 1: row statistics.
-// A row (one lattice cell's V logits) is owned by an aligned group of LPR lanes; a warp owns
-// 32/LPR consecutive rows, so a warp-wide load instruction covers one contiguous span of memory
-// (coalesced) for any V.  LPR = 32: one row per warp, UNR independent 16-B loads in flight per lane.
-// Each lane keeps an online (max, sum) pair and rescales only when its running max moves.
+// Pass 1, long rows: ONE CTA PER ROW, non-persistent grid (grid = N*T*U blocks of 256 threads).
+// Measured on B200 (tools/probe/bw_probe.cu): a short-lived block that issues all its loads and
+// retires streams 8 GB at 7.5 TB/s, a persistent grid-stride loop over the same bytes at 7.1 TB/s
+// (read) / 6.0 vs 6.85 TB/s (read+write) - block turnover keeps the DRAM access window compact.
+// Thread i owns vectors i, i+256, ... (NV per trip, all loads issued before first use; one trip
+// when V/VEC <= 256*NV, i.e. V <= 8192 in fp32).  Per trip the statistics are the exact two-pass
+// max / sum exp(x-max) from registers; trips are merged online.  Block combine: warp shuffles, one
+// shared-memory exchange, one __syncthreads.
 // =================================================================================================
-template <typename T, int VEC, int LPR, int UNR>
-__global__ void __launch_bounds__(256)
-rowstats_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
-                const int* __restrict__ xlen, const int* __restrict__ ylen,
-                typename Real<T>::pair* __restrict__ stat, typename Real<T>::pair* __restrict__ lp2,
-                const Dims d) {
-    using R = Real<T>;
-    constexpr int RPW = kWarp / LPR;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LPR, sl = lane % LPR;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int nv = d.V / VEC;
+constexpr int kRowThreads = 256;
 
-    for (uint64_t r0 = (uint64_t)gw * RPW; r0 < d.rows; r0 += (uint64_t)warps_total * RPW) {
-        const uint32_t r = (uint32_t)r0 + sub;
-        bool valid = r < d.rows;
-        uint32_t bt = 0, u = 0, b = 0, t = 0;
-        int Tb = 0, Ub = 0;
-        if (valid) {
-            d.divU.divmod(r, bt, u);
-            d.divT.divmod(bt, b, t);
-            utt_extent(d, xlen, ylen, b, Tb, Ub);
-            valid = (int)t < Tb && (int)u < Ub;
-        }
-        T m = R::neg_inf(), s = 0;
-        const T* row = acts + (uint64_t)r * d.V;
-        if (valid) {
-            for (int i0 = sl; i0 < nv; i0 += LPR * UNR) {
-                VecT<T, VEC> x[UNR];
+template <typename T, int VEC, int NV>
+__global__ void __launch_bounds__(kRowThreads)
+rowstats_row_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
+                    const int* __restrict__ xlen, const int* __restrict__ ylen,
+                    typename Real<T>::pair* __restrict__ stat, typename Real<T>::pair* __restrict__ lp2,
+                    const Dims d) {
+    using R = Real<T>;
+    __shared__ T sh_m[kRowThreads / 32], sh_s[kRowThreads / 32];
+    const uint32_t r = blockIdx.x;
+    uint32_t bt, u, b, t;
+    d.divU.divmod(r, bt, u);
+    d.divT.divmod(bt, b, t);
+    int Tb, Ub;
+    utt_extent(d, xlen, ylen, b, Tb, Ub);
+    if ((int)t >= Tb || (int)u >= Ub) return;  // padded cell: nothing to read (block-uniform)
+    const int nv = d.V / VEC;
+    const T* row = acts + (uint64_t)r * d.V;
+    T m = R::neg_inf(), s = 0;
+    for (int base = threadIdx.x; base < nv; base += kRowThreads * NV) {
+        VecT<T, VEC> x[NV];
 #pragma unroll
-                for (int j = 0; j < UNR; ++j) {
-                    const int i = i0 + j * LPR;
-                    if (i < nv) {
-                        x[j] = ld_keep<T, VEC>(row + (size_t)i * VEC);
-                    } else {
+        for (int j = 0; j < NV; ++j) {
+            const int i = base + j * kRowThreads;
+            if (i < nv) {
+                x[j] = ld_keep<T, VEC>(row + (size_t)i * VEC);
+            } else {
 #pragma unroll
-                        for (int c = 0; c < VEC; ++c) x[j].v[c] = R::neg_inf();
-                    }
-                }
-                T vm = x[0].v[0];
-#pragma unroll
-                for (int j = 0; j < UNR; ++j)
-#pragma unroll
-                    for (int c = 0; c < VEC; ++c) vm = x[j].v[c] > vm ? x[j].v[c] : vm;
-                if (vm > m) {  // running max moved: rescale the partial sum (rare after the first trips)
-                    s *= R::exp(m - vm);  // m = -inf -> exp(-inf) = 0, s was 0
-                    m = vm;
-                }
-                const T mm = (m == R::neg_inf()) ? T(0) : m;  // all -inf so far: keep exp() at 0, not NaN
-#pragma unroll
-                for (int j = 0; j < UNR; ++j)
-#pragma unroll
-                    for (int c = 0; c < VEC; ++c) s += R::exp(x[j].v[c] - mm);
+                for (int c = 0; c < VEC; ++c) x[j].v[c] = R::neg_inf();
             }
         }
-        // combine the LPR lanes of the row: global max first, one rescale per lane, then the sum
-        const T M = group_max<LPR>(m);
-        const T sc = (m == R::neg_inf()) ? T(0) : s * R::exp(m - M);
-        const T S = group_sum<LPR>(sc);
-        if (valid && sl == 0) {
+        T vm = x[0].v[0];
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) vm = x[j].v[c] > vm ? x[j].v[c] : vm;
+        if (vm > m) {
+            s *= R::exp(m - vm);
+            m = vm;
+        }
+        const T mm = (m == R::neg_inf()) ? T(0) : m;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) s += R::exp(x[j].v[c] - mm);
+    }
+    // warp combine, then the 8 warp results through shared memory
+    const T Mw = group_max<32>(m);
+    const T Sw = group_sum<32>((m == R::neg_inf()) ? T(0) : s * R::exp(m - Mw));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh_m[warp] = Mw;
+        sh_s[warp] = Sw;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int NW = kRowThreads / 32;
+        const T mw = lane < NW ? sh_m[lane] : R::neg_inf();
+        const T sw = lane < NW ? sh_s[lane] : T(0);
+        const T M = group_max<NW>(mw);
+        const T S = group_sum<NW>((mw == R::neg_inf()) ? T(0) : sw * R::exp(mw - M));
+        if (lane == 0) {
             const T lse = R::log(S);
             typename R::pair st;
             st.x = M;
@@ -146,13 +151,13 @@ rowstats_tile_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
     constexpr int RPW = kWarp / LPR;
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPR, sl = lane % LPR;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nv = d.V / VEC;
 
-    for (uint64_t r0 = (uint64_t)gw * RPW; r0 < d.rows; r0 += (uint64_t)warps_total * RPW) {
+    {   // non-persistent: one tile of RPW rows per warp (see rowstats_row_kernel for why)
+        const uint64_t r0 = gw * RPW;
         const uint32_t r = (uint32_t)r0 + sub;
-        bool valid = r < d.rows;
+        bool valid = r0 + sub < d.rows;
         uint32_t bt = 0, u = 0, b = 0, t = 0;
         int Tb = 0, Ub = 0;
         if (valid) {
@@ -418,66 +423,56 @@ __device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, 
 }
 
 
-// Pass 2, long rows: one row per warp, UNR 16-B vectors per lane per trip, software-pipelined —
-// the next trip's loads (and the row's lattice constants) are in flight while the current trip is
-// exponentiated and stored.
-template <typename T, int VEC, int UNR, bool SCALED, int POL = 0>
-__global__ void __launch_bounds__(256)
-grad_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
-            const int* __restrict__ xlen, const int* __restrict__ ylen,
-            const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
-            const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
-            const Dims d) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Pass 2, long rows: one CTA per row, non-persistent (same reasoning as rowstats_row_kernel).  All
+// of a thread's loads are issued before the row's lattice constants are fetched, so both latencies
+// overlap; measured shape of this loop (probe): 6.85 TB/s read+write at V = 5000.
+template <typename T, int VEC, int NV, bool SCALED>
+__global__ void __launch_bounds__(kRowThreads)
+grad_row_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
+                const int* __restrict__ xlen, const int* __restrict__ ylen,
+                const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
+                const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
+                const Dims d) {
+    const uint32_t r = d.rows - 1 - blockIdx.x;
+    uint32_t bt, u, b, t;
+    d.divU.divmod(r, bt, u);
+    d.divT.divmod(bt, b, t);
+    int Tb, Ub;
+    utt_extent(d, xlen, ylen, b, Tb, Ub);
     const int nv = d.V / VEC;
     const int kb = d.blank;
-    constexpr int STEP = kWarp * UNR;
-
-    for (uint64_t rr = gw; rr < d.rows; rr += warps_total) {
-        const uint32_t r = d.rows - 1 - (uint32_t)rr;
-        uint32_t bt, u, b, t;
-        d.divU.divmod(r, bt, u);
-        d.divT.divmod(bt, b, t);
-        int Tb, Ub;
-        utt_extent(d, xlen, ylen, b, Tb, Ub);
-        const T* row = acts + (uint64_t)r * d.V;
-        T* grow = grads + (uint64_t)r * d.V;
-        if ((int)t >= Tb || (int)u >= Ub) {
-            VecT<T, VEC> z;
+    const T* row = acts + (uint64_t)r * d.V;
+    T* grow = grads + (uint64_t)r * d.V;
+    if ((int)t >= Tb || (int)u >= Ub) {
+        VecT<T, VEC> z;
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) z.v[c] = 0;
-            for (int i = lane; i < nv; i += kWarp) st_stream<T, VEC>(grow + (size_t)i * VEC, z);
-            continue;
+        for (int c = 0; c < VEC; ++c) z.v[c] = 0;
+        for (int i = threadIdx.x; i < nv; i += kRowThreads) st_stream<T, VEC>(grow + (size_t)i * VEC, z);
+        return;
+    }
+    VecT<T, VEC> x[NV];
+    auto load = [&](int base) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = base + j * kRowThreads;
+            if (i < nv) x[j] = ld_stream<T, VEC>(row + (size_t)i * VEC);
         }
-        VecT<T, VEC> xa[UNR], xb[UNR];
-        auto load = [&](VecT<T, VEC>(&x)[UNR], int i0) {
+    };
+    load(threadIdx.x);  // in flight before the lattice constants are fetched
+    const RowGrad<T> rg = row_grad_setup<T>(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
+    auto emit = [&](int base) {
 #pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-                const int i = i0 + j * kWarp;
-                if (i < nv) x[j] = (POL & 1) ? ld_keep<T, VEC>(row + (size_t)i * VEC) : ld_stream<T, VEC>(row + (size_t)i * VEC);
-            }
-        };
-        load(xa, lane);  // first trip is in flight before the lattice constants are fetched
-        const RowGrad<T> rg = row_grad_setup<T>(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
-        auto emit = [&](const VecT<T, VEC>(&x)[UNR], int i0) {
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-                const int i = i0 + j * kWarp;
-                if (i < nv) {
-                    const VecT<T, VEC> g = grad_vec<T, VEC, SCALED>(x[j], rg, i * VEC, kb, scale);
-                    if (POL & 2) *reinterpret_cast<VecT<T, VEC>*>(grow + (size_t)i * VEC) = g;
-                    else st_stream<T, VEC>(grow + (size_t)i * VEC, g);
-                }
-            }
-        };
-        for (int i0 = lane; i0 < nv; i0 += 2 * STEP) {
-            load(xb, i0 + STEP);
-            emit(xa, i0);
-            load(xa, i0 + 2 * STEP);
-            emit(xb, i0 + STEP);
+        for (int j = 0; j < NV; ++j) {
+            const int i = base + j * kRowThreads;
+            if (i < nv)
+                st_stream<T, VEC>(grow + (size_t)i * VEC,
+                                  grad_vec<T, VEC, SCALED>(x[j], rg, i * VEC, kb, scale));
         }
+    };
+    emit(threadIdx.x);
+    for (int base = threadIdx.x + kRowThreads * NV; base < nv; base += kRowThreads * NV) {  // V > 256*NV*VEC only
+        load(base);
+        emit(base);
     }
 }
 
@@ -492,13 +487,12 @@ grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* _
     constexpr int RPW = kWarp / LPR;
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPR, sl = lane % LPR;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nv = d.V / VEC;
     const int kb = d.blank;
 
-    for (uint64_t r0 = (uint64_t)gw * RPW; r0 < d.rows; r0 += (uint64_t)warps_total * RPW) {
-        const uint64_t rr = r0 + sub;
+    do {   // non-persistent: one tile of RPW rows per warp
+        const uint64_t rr = gw * RPW + sub;
         if (rr >= d.rows) continue;
         const uint32_t r = d.rows - 1 - (uint32_t)rr;
         uint32_t bt, u, b, t;
@@ -533,7 +527,7 @@ grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* _
                 st_stream<T, VEC>(grow + (size_t)i * VEC,
                                   grad_vec<T, VEC, SCALED>(x[j], rg, i * VEC, kb, scale));
         }
-    }
+    } while (false);
 }
 
 }  // namespace b200rnnt

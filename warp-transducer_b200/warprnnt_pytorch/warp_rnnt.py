@@ -53,6 +53,8 @@ _lib.rnnt_b200_set_profiling.restype = None
 _lib.rnnt_b200_set_profiling.argtypes = [C.c_int]
 _lib.rnnt_b200_last_kernel_ms.restype = C.c_int
 _lib.rnnt_b200_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
+_lib.rnnt_b200_profile_collect.restype = C.c_int
+_lib.rnnt_b200_profile_collect.argtypes = [C.POINTER(C.c_float)]
 
 
 def lib():
@@ -156,6 +158,13 @@ def gpu_rnnt_async(acts, labels, input_lengths, label_lengths, costs, grads, bla
     if st != RNNT_STATUS_SUCCESS:
         raise RuntimeError("compute_rnnt_loss_async failed: " + status_string(st))
     return workspace
+
+
+def profile_collect():
+    """(calls, (rowstats, lattice, grad) mean ms) over the profiled calls since the last collect."""
+    out = (C.c_float * 3)()
+    n = _lib.rnnt_b200_profile_collect(out)
+    return n, tuple(out)
 
 
 def cpu_rnnt(acts, labels, input_lengths, label_lengths, costs, grads, blank_label, num_threads):
