@@ -54,8 +54,11 @@ __device__ __forceinline__ void utt_extent(const Dims& d, const int* __restrict_
 // =================================================================================================
 constexpr int kRowThreads = 256;
 
+#ifndef RNNT_ROWSTATS_MINB
+#define RNNT_ROWSTATS_MINB 7
+#endif
 template <typename T, int VEC, int NV>
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(kRowThreads, RNNT_ROWSTATS_MINB)
 rowstats_row_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
                     const int* __restrict__ xlen, const int* __restrict__ ylen,
                     typename Real<T>::pair* __restrict__ stat, typename Real<T>::pair* __restrict__ lp2,
@@ -426,8 +429,11 @@ __device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, 
 // Pass 2, long rows: one CTA per row, non-persistent (same reasoning as rowstats_row_kernel).  All
 // of a thread's loads are issued before the row's lattice constants are fetched, so both latencies
 // overlap; measured shape of this loop (probe): 6.85 TB/s read+write at V = 5000.
+#ifndef RNNT_GRAD_MINB
+#define RNNT_GRAD_MINB 5
+#endif
 template <typename T, int VEC, int NV, bool SCALED>
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(kRowThreads, RNNT_GRAD_MINB)
 grad_row_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
                 const int* __restrict__ xlen, const int* __restrict__ ylen,
                 const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
