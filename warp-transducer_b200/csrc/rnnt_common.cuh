@@ -69,6 +69,36 @@ template <> struct Real<double> {
 };
 
 // ---------------------------------------------------------------------------------------------
+// sum_k exp(x_k - M) for a known row maximum M, and the log of the sum.
+// float: one FFMA + MUFU.EX2 per element, 2^(x*log2e - fl(M*log2e)); the rounding of the product
+// M*log2e is recovered exactly with one FMA per row (comp) and folded into the logarithm, so the
+// result equals the (x - M) form to fp32 rounding even for |M| ~ 1e3.  double: plain exp/log.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct ExpSum;
+template <> struct ExpSum<float> {
+    float negML, comp;
+    __device__ __forceinline__ explicit ExpSum(float M) {
+        const float ML = M * Real<float>::kLog2e;
+        negML = -ML;
+        comp = fmaf(M, Real<float>::kLog2e, negML);  // M*log2e - fl(M*log2e), exact
+    }
+    __device__ __forceinline__ float term(float x) const {
+        return Real<float>::exp2(fmaf(x, Real<float>::kLog2e, negML));
+    }
+    __device__ __forceinline__ float log_of(float S) const {
+        float l;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(S));
+        return (l - comp) * 0.6931471805599453f;
+    }
+};
+template <> struct ExpSum<double> {
+    double M;
+    __device__ __forceinline__ explicit ExpSum(double m) : M(m) {}
+    __device__ __forceinline__ double term(double x) const { return ::exp(x - M); }
+    __device__ __forceinline__ double log_of(double S) const { return ::log(S); }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Vectorised global access with cache policy.  BYTES in {4, 8, 16}.
 //   ld_keep   : read-only path, normal L2 residency (first pass over the logits: on shapes that fit
 //               the 126 MB L2 the second pass then hits)

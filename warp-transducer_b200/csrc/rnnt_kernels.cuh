@@ -187,15 +187,15 @@ rowstats_tile_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
 #pragma unroll
             for (int c = 0; c < VEC; ++c) m = x[j].v[c] > m ? x[j].v[c] : m;
         const T M = group_max<LPR>(m);
-        const T Mz = (M == R::neg_inf()) ? T(0) : M;
+        const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
         T s = 0;
 #pragma unroll
         for (int j = 0; j < kVPL; ++j)
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) s += R::exp(x[j].v[c] - Mz);
+            for (int c = 0; c < VEC; ++c) s += es.term(x[j].v[c]);
         const T S = group_sum<LPR>(s);
         if (valid && sl == 0) {
-            const T lse = R::log(S);
+            const T lse = es.log_of(S);
             typename R::pair st;
             st.x = M;
             st.y = lse;
@@ -279,26 +279,30 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
     utt_extent(d, xlen, ylen, b, Tb, Ub);
     const size_t base = (size_t)b * lattice_block(d);
     const int last = Tb + Ub - 2;
-    const bool mine = u < Ub;
     const int mU = d.maxU;
-    const P* lp_u = lp2 + base + u;  // diagonal-major: lp_u[n*mU] = cell (n-u, u)
-
-    // copy this thread's cell of diagonal dg into the ring (no-op outside the lattice); the commit
-    // is unconditional so every thread's group count advances in lock step with the step index
-    auto issue = [&](int dg) {
-        const int t = dg - u;
-        if (mine && dg >= 0 && dg <= last && t >= 0 && t < Tb)
-            cp_async<sizeof(P)>(&ring[(dg & (kRing - 1)) * NT + u], lp_u + (size_t)dg * mU);
-        cp_async_commit();
-    };
+    // thread u owns one cell on each diagonal dg with 0 <= dg - u < width (width = 0: no column)
+    const unsigned width = u < Ub ? (unsigned)Tb : 0u;
+    const P* lp_u = lp2 + base + u;  // diagonal-major: lp_u[dg*mU] = cell (dg-u, u)
+    const unsigned ring_elems = kRing * NT;
+    // All per-step addresses are carried as running pointers / wrapped slot offsets: the step loop
+    // is one warp per scheduler, so every integer instruction is exposed latency.
 
     if (blockIdx.y == 0) {
         // ------------------------------------------------------------------ alpha
-        double* al_u = alphas + base + u;
+        double* sp = alphas + base + u;  // store pointer, advances one diagonal per step
         double a = (u == 0) ? 0.0 : NINF;  // alpha(t-1, u) of this thread's column
-        if (u == 0) al_u[0] = 0.0;
+        if (u == 0) *sp = 0.0;
+        const P* gp = lp_u;  // next diagonal to fetch
+        unsigned fslot = u, fdg = 0;
 #pragma unroll
-        for (int k = 0; k < kRing - 1; ++k) issue(k);
+        for (int k = 0; k < kRing - 1; ++k) {
+            if (fdg - (unsigned)u < width) cp_async<sizeof(P)>(&ring[fslot], gp);
+            cp_async_commit();
+            gp += mU;
+            ++fdg;
+            fslot += NT;
+        }
+        unsigned rslot = u;  // slot of diagonal n-1
         for (int n = 1; n <= last; ++n) {
             cp_async_wait<kRing - 2>();  // diagonal n-1 has landed (this thread's part)
             if (MULTI) {
@@ -307,17 +311,25 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
             } else {
                 __syncwarp();
             }
-            issue(n + kRing - 2);  // reuses the slot of diagonal n-2, which nobody reads any more
+            // fetch diagonal n+kRing-2 into the slot of diagonal n-2, which nobody reads any more
+            if (fdg - (unsigned)u < width) cp_async<sizeof(P)>(&ring[fslot], gp);
+            cp_async_commit();
+            gp += mU;
+            ++fdg;
+            fslot += NT;
+            if (fslot >= ring_elems) fslot -= ring_elems;
             double a_left = __shfl_up_sync(0xffffffffu, a, 1);
             if (MULTI && lane == 0 && warp > 0) a_left = edge[n & 1][warp - 1];
-            const int t = n - u;
-            if (mine && t >= 0 && t < Tb) {
-                const P* slot = ring + ((n - 1) & (kRing - 1)) * NT + u;
-                const T sx = t > 0 ? slot[0].x : T(0);                   // lp_blank(t-1, u)
+            sp += mU;
+            if ((unsigned)(n - u) < width) {
+                const P* slot = ring + rslot;
+                const T sx = n > u ? slot[0].x : T(0);                   // lp_blank(t-1, u)
                 const T ey = u > 0 ? slot[-1].y : Real<T>::neg_inf();    // lp_label(t, u-1)
                 a = lse2<T>(a + (double)sx, a_left + (double)ey);
-                al_u[(size_t)n * mU] = a;
+                *sp = a;
             }
+            rslot += NT;
+            if (rslot >= ring_elems) rslot -= ring_elems;
         }
         if (u == Ub - 1) {
             cp_async_wait<0>();
@@ -327,26 +339,43 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
         }
     } else {
         // ------------------------------------------------------------------ beta
-        double* be_u = betas + base + u;
+        double* sp = betas + base + u + (size_t)last * mU;
         double bv = (u == Ub - 1) ? 0.0 : NINF;  // beta(t+1, u); virtual beta(T, U-1) = 0
+        const P* gp = lp_u + (size_t)last * mU;
+        unsigned fslot = (unsigned)(last & (kRing - 1)) * NT + u;
+        int fdg = last;
+        const unsigned rstart = fslot;
 #pragma unroll
-        for (int k = 0; k < kRing - 1; ++k) issue(last - k);
+        for (int k = 0; k < kRing - 1; ++k) {
+            if ((unsigned)(fdg - u) < width) cp_async<sizeof(P)>(&ring[fslot], gp);
+            cp_async_commit();
+            gp -= mU;
+            --fdg;
+            fslot = fslot >= (unsigned)NT ? fslot - NT : fslot + ring_elems - NT;
+        }
+        unsigned rslot = rstart;  // slot of diagonal n
         for (int n = last; n >= 0; --n) {
             cp_async_wait<kRing - 2>();  // this thread's cell of diagonal n has landed
             if (MULTI) {
                 if (lane == 0) edge[n & 1][warp] = bv;
                 __syncthreads();
             }
-            issue(n - (kRing - 1));  // slot of diagonal n+1: written and read by this thread only
+            // slot of diagonal n+1: written and read by this thread only
+            if ((unsigned)(fdg - u) < width) cp_async<sizeof(P)>(&ring[fslot], gp);
+            cp_async_commit();
+            gp -= mU;
+            --fdg;
+            fslot = fslot >= (unsigned)NT ? fslot - NT : fslot + ring_elems - NT;
             double b_right = __shfl_down_sync(0xffffffffu, bv, 1);
             if (MULTI && lane == 31 && warp + 1 < nwarps) b_right = edge[n & 1][warp + 1];
-            const int t = n - u;
-            if (mine && t >= 0 && t < Tb) {
-                const P p = ring[(n & (kRing - 1)) * NT + u];
+            if ((unsigned)(n - u) < width) {
+                const P p = ring[rslot];
                 const T py = u < Ub - 1 ? p.y : Real<T>::neg_inf();
                 bv = lse2<T>(bv + (double)p.x, b_right + (double)py);
-                be_u[(size_t)n * mU] = bv;
+                *sp = bv;
             }
+            sp -= mU;
+            rslot = rslot >= (unsigned)NT ? rslot - NT : rslot + ring_elems - NT;
         }
         if (u == 0) llb[b] = bv;
     }
