@@ -149,6 +149,37 @@ rnntStatus_t compute_rnnt_loss_async_fp64(const double* const activations, doubl
                                           int minibatch, double* costs_device, double grad_scale,
                                           void* workspace, struct rnntOptions options);
 
+/*
+ * Training-step split used by warprnnt_pytorch: the gradient pass runs in
+ * autograd's backward with the upstream gradient folded in, so the framework never makes a
+ * separate pass over the [N,T,U,V] tensor (the reference multiplies it in place afterwards,
+ * pytorch_binding/warprnnt_pytorch/__init__.py:47-50).  All pointers DEVICE, no synchronisation.
+ *
+ *   rnnt_b200_forward   log-softmax statistics + alpha (+ beta when prepare_backward != 0) lattices
+ *                       into `workspace`, costs_device[minibatch] = -log-likelihood.
+ *   rnnt_b200_backward  gradient pass only, from the SAME workspace and the same activations:
+ *                       gradients[b,...] = grad_scale * grad_costs_device[b] * d cost[b]/d logits
+ *                       (grad_costs_device may be NULL = all ones).  Zeros on padding.
+ */
+rnntStatus_t rnnt_b200_forward(const float* const activations, const int* const flat_labels,
+                               const int* const label_lengths, const int* const input_lengths,
+                               int alphabet_size, int minibatch, float* costs_device,
+                               int prepare_backward, void* workspace, struct rnntOptions options);
+rnntStatus_t rnnt_b200_forward_fp64(const double* const activations, const int* const flat_labels,
+                                    const int* const label_lengths, const int* const input_lengths,
+                                    int alphabet_size, int minibatch, double* costs_device,
+                                    int prepare_backward, void* workspace, struct rnntOptions options);
+rnntStatus_t rnnt_b200_backward(const float* const activations, float* gradients,
+                                const int* const flat_labels, const int* const label_lengths,
+                                const int* const input_lengths, int alphabet_size, int minibatch,
+                                const float* grad_costs_device, float grad_scale, void* workspace,
+                                struct rnntOptions options);
+rnntStatus_t rnnt_b200_backward_fp64(const double* const activations, double* gradients,
+                                     const int* const flat_labels, const int* const label_lengths,
+                                     const int* const input_lengths, int alphabet_size,
+                                     int minibatch, const double* grad_costs_device,
+                                     double grad_scale, void* workspace, struct rnntOptions options);
+
 /* Number of kernels the last compute call on this thread launched (bench.py's gpu_launches). */
 int rnnt_b200_last_launch_count(void);
 

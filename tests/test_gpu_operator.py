@@ -118,3 +118,51 @@ def test_reference_style_gpu_rnnt_call():
     assert np.allclose(grads.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)
     with pytest.raises(RuntimeError):
         warp_rnnt.cpu_rnnt(acts.cpu(), None, None, None, costs, grads.cpu(), 0, 0)
+
+
+def test_side_stream_retain_graph_and_forward_only():
+    """backward twice (retain_graph) accumulates; the op honours the current (non-default) stream;
+    no-grad inputs skip the beta lattice but return the same costs."""
+    from warprnnt_pytorch import RNNTLoss
+    rng = np.random.default_rng(5)
+    N, T, U, V = 3, 10, 5, 64
+    acts_np = rng.standard_normal((N, T, U, V)).astype(np.float32)
+    labels_np = rng.integers(1, V, size=(N, U - 1)).astype(np.int32)
+    tl_np = np.array([T, 7, 9], np.int32)
+    ul_np = np.array([U - 1, 1, 3], np.int32)
+    c_ref, g_ref, _ = pyoracle.rnnt_logits(acts_np.astype(np.float64), labels_np, tl_np, ul_np, 0)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        acts = torch.tensor(acts_np, device="cuda", requires_grad=True)
+        labels, tl, ul = (torch.as_tensor(x).cuda() for x in (labels_np, tl_np, ul_np))
+        loss = RNNTLoss(reduction='sum')(acts, labels, tl, ul)
+        loss.backward(retain_graph=True)
+        loss.backward()
+        no_grad = RNNTLoss(reduction='none')(acts.detach(), labels, tl, ul)
+    side.synchronize()
+    assert np.allclose(loss.item(), c_ref.sum(), rtol=1e-5)
+    assert np.allclose(acts.grad.cpu().numpy(), 2 * g_ref, rtol=1e-4, atol=2e-6)
+    assert np.allclose(no_grad.cpu().numpy(), c_ref, rtol=1e-5)
+
+
+def test_forward_backward_split_matches_full_call():
+    """rnnt_b200_forward + rnnt_b200_backward == compute_rnnt_loss_async, bit for bit at scale 1,
+    and per-utterance grad_costs scale rows of the gradient."""
+    from warprnnt_pytorch import warp_rnnt as wr
+    rng = np.random.default_rng(6)
+    N, T, U, V = 4, 9, 6, 300
+    acts = torch.tensor(rng.standard_normal((N, T, U, V)).astype(np.float32), device="cuda")
+    labels = torch.as_tensor(rng.integers(1, V, size=(N, U - 1)).astype(np.int32)).cuda()
+    tl = torch.tensor([T, 5, 9, 3], dtype=torch.int32).cuda()
+    ul = torch.tensor([U - 1, 0, 2, 5], dtype=torch.int32).cuda()
+    c_full, g_full = torch.empty(N, device="cuda"), torch.empty_like(acts)
+    wr.gpu_rnnt_async(acts, labels, tl, ul, c_full, g_full, 0)
+    c_split, g_split = torch.empty(N, device="cuda"), torch.full_like(acts, float("nan"))
+    ws = wr.gpu_rnnt_forward(acts, labels, tl, ul, c_split, 0, prepare_backward=True)
+    wr.gpu_rnnt_backward(acts, labels, tl, ul, g_split, None, 0, 1.0, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(c_full, c_split) and torch.equal(g_full, g_split)
+    w = torch.tensor([2.0, -1.0, 0.0, 0.5], device="cuda")
+    wr.gpu_rnnt_backward(acts, labels, tl, ul, g_split, w, 0, 0.25, ws)
+    torch.cuda.synchronize()
+    assert torch.allclose(g_split, g_full * (0.25 * w).view(-1, 1, 1, 1), rtol=1e-6, atol=0)

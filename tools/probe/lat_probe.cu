@@ -16,7 +16,8 @@ template <int OP> __global__ void k(double* out, long long* cyc, double seed, fl
         if (OP == 5) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(f));
         if (OP == 6) f = __shfl_up_sync(0xffffffffu, f, 1);
         if (OP == 7) a = __shfl_up_sync(0xffffffffu, a, 1);
-        if (OP == 8) { f = (float)a; asm volatile("" : "+f"(f)); a = (double)f; }  // both conversions
+        if (OP == 8) { asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f) : "d"(a)); asm volatile("cvt.f64.f32 %0, %1;" : "=d"(a) : "f"(f)); }  // both conversions
+        if (OP == 12) { float h = f + g; float e = h - f; float lo = g - e; f = h + lo; }  // fast two-sum chain (3 dependent FADD)
         if (OP == 9) a = fmax(a, b) + 1e-9;                       // DSETP/select + DADD
         if (OP == 10) f = fmaf(f, g, g);
         if (OP == 11) { asm volatile("bar.sync 0;"); f += 1.f; }
@@ -27,9 +28,9 @@ template <int OP> __global__ void k(double* out, long long* cyc, double seed, fl
 }
 int main() {
     double* out; long long* cyc; cudaMalloc(&out, 8192); cudaMallocManaged(&cyc, 8);
-    const char* names[] = {"DADD", "DFMA", "F2F.f32<-f64 + F2F.f64<-f32 + DADD", "FADD", "MUFU.EX2", "MUFU.LG2", "SHFL f32", "SHFL f64 (2x32)", "F2F both ways", "fmax(double)+DADD", "FFMA", "BAR.SYNC(320 thr)+FADD"};
+    const char* names[] = {"DADD", "DFMA", "F2F.f32<-f64 + F2F.f64<-f32 + DADD", "FADD", "MUFU.EX2", "MUFU.LG2", "SHFL f32", "SHFL f64 (2x32)", "F2F both ways", "fmax(double)+DADD", "FFMA", "BAR.SYNC(320 thr)+FADD", "two-sum (4 FADD)"};
 #define RUN(OP, TH) k<OP><<<1, TH>>>(out, cyc, 1.5, 0.5f); cudaDeviceSynchronize(); k<OP><<<1, TH>>>(out, cyc, 1.5, 0.5f); cudaDeviceSynchronize(); printf("%-40s %6.1f cycles/iter (%d threads)\n", names[OP], (double)cyc[0] / N, TH);
     RUN(0, 32) RUN(1, 32) RUN(2, 32) RUN(3, 32) RUN(4, 32) RUN(5, 32) RUN(6, 32) RUN(7, 32) RUN(8, 32) RUN(9, 32) RUN(10, 32) RUN(11, 320) RUN(11, 64)
-    RUN(0, 320) RUN(8, 320)
+    RUN(0, 320) RUN(8, 320) RUN(12, 32)
     return 0;
 }

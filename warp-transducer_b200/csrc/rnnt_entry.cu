@@ -135,11 +135,12 @@ void launch_rowstats_row(const T* acts, const int* labels, const int* xlen, cons
 
 template <typename T, int VEC, int NV>
 void launch_grad_row(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
-                     const Workspace& w, T scale, const Dims& d, cudaStream_t s) {
-    auto k = scale != T(1) ? grad_row_kernel<T, VEC, NV, true> : grad_row_kernel<T, VEC, NV, false>;
+                     const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s) {
+    auto k = (scale != T(1) || scale_vec) ? grad_row_kernel<T, VEC, NV, true>
+                                          : grad_row_kernel<T, VEC, NV, false>;
     k<<<d.rows, kRowThreads, 0, s>>>(acts, grads, labels, xlen, ylen,
                                       static_cast<const typename Real<T>::pair*>(w.stat), w.alphas,
-                                      w.betas, w.llf, scale, d);
+                                      w.betas, w.llf, scale, scale_vec, d);
     ++g_last_launches;
 }
 
@@ -155,12 +156,13 @@ void launch_rowstats_tile(const T* acts, const int* labels, const int* xlen, con
 
 template <typename T, int VEC, int LPR>
 void launch_grad_tile(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
-                      const Workspace& w, T scale, const Dims& d, cudaStream_t s) {
-    auto k = scale != T(1) ? grad_tile_kernel<T, VEC, LPR, true> : grad_tile_kernel<T, VEC, LPR, false>;
+                      const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s) {
+    auto k = (scale != T(1) || scale_vec) ? grad_tile_kernel<T, VEC, LPR, true>
+                                          : grad_tile_kernel<T, VEC, LPR, false>;
     const uint64_t warps = ((uint64_t)d.rows * LPR + 31) / 32;
     k<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(acts, grads, labels, xlen, ylen,
                                                   static_cast<const typename Real<T>::pair*>(w.stat),
-                                                  w.alphas, w.betas, w.llf, scale, d);
+                                                  w.alphas, w.betas, w.llf, scale, scale_vec, d);
     ++g_last_launches;
 }
 
@@ -179,14 +181,14 @@ inline int pick_lpr(int nv) {
 
 template <typename T, int VEC>
 void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
-                   const Workspace& w, T scale, const Dims& d, cudaStream_t s, int pass) {
+                   const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s, int pass) {
     const int nv = d.V / VEC;
     if (nv > 32 * kVPL) {  // long rows: CTA per row; NV = vectors per thread per trip
         const int per_thread = (nv + kRowThreads - 1) / kRowThreads;
 #define B200_ROW(NVV)                                                                             \
     do {                                                                                          \
         if (pass == 1) launch_rowstats_row<T, VEC, NVV>(acts, labels, xlen, ylen, w, d, s);       \
-        else launch_grad_row<T, VEC, NVV>(acts, grads, labels, xlen, ylen, w, scale, d, s);       \
+        else launch_grad_row<T, VEC, NVV>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s);       \
     } while (0)
         if (sizeof(T) == 4 && VEC == 4) {  // the fp32 fast path gets an exact register count
             switch (per_thread) {
@@ -209,7 +211,7 @@ void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, 
 #define B200_TILE(L)                                                                              \
     case L:                                                                                       \
         if (pass == 1) launch_rowstats_tile<T, VEC, L>(acts, labels, xlen, ylen, w, d, s);        \
-        else launch_grad_tile<T, VEC, L>(acts, grads, labels, xlen, ylen, w, scale, d, s);        \
+        else launch_grad_tile<T, VEC, L>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s);        \
         break;
     switch (pick_lpr(nv)) {
         B200_TILE(2)
@@ -223,26 +225,32 @@ void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, 
 
 template <typename T>
 void stream_pass(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
-                 const Workspace& w, T scale, const Dims& d, cudaStream_t s, int pass) {
+                 const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s, int pass) {
     // widest vector the row pitch and the base pointers allow
     const uintptr_t mis = reinterpret_cast<uintptr_t>(acts) | reinterpret_cast<uintptr_t>(grads) |
                           ((uintptr_t)d.V * sizeof(T));
     constexpr int kMaxVec = 16 / sizeof(T);
     if (mis % 16 == 0)
-        stream_passes<T, kMaxVec>(acts, grads, labels, xlen, ylen, w, scale, d, s, pass);
+        stream_passes<T, kMaxVec>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
     else if (sizeof(T) == 4 && mis % 8 == 0)
-        stream_passes<T, (kMaxVec > 2 ? 2 : 1)>(acts, grads, labels, xlen, ylen, w, scale, d, s, pass);
+        stream_passes<T, (kMaxVec > 2 ? 2 : 1)>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
     else
-        stream_passes<T, 1>(acts, grads, labels, xlen, ylen, w, scale, d, s, pass);
+        stream_passes<T, 1>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
 }
 
 // ---- the path -----------------------------------------------------------------------------------
+// What a call does.  The reference API is FULL (stats -> lattice -> grad in one call); the
+// operator splits a training step into FORWARD (stats + both lattices, costs out) and BACKWARD
+// (gradient pass only, reading the lattices the forward left in the workspace).
+enum Phase { kFull = 0, kForward = 1, kBackward = 2 };
+
 template <typename T>
 rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, const int* xlen,
-                 int V, int N, T* costs, bool async, T scale, void* workspace, rnntOptions opt) {
+                 int V, int N, T* costs, bool async, T scale, const T* scale_vec, Phase phase,
+                 bool want_beta, void* workspace, rnntOptions opt) {
     if (acts == nullptr || labels == nullptr || ylen == nullptr || xlen == nullptr ||
-        costs == nullptr || workspace == nullptr || V <= 0 || N <= 0 || opt.maxT <= 0 ||
-        opt.maxU <= 0)
+        (costs == nullptr && phase != kBackward) || workspace == nullptr || V <= 0 || N <= 0 ||
+        opt.maxT <= 0 || opt.maxU <= 0 || (phase == kBackward && grads == nullptr))
         return RNNT_STATUS_INVALID_VALUE;  // reference src/rnnt_entrypoint.cpp:49-59
     if (opt.loc == RNNT_CPU) {
         fprintf(stderr, "b200-rnnt: CPU execution requested, but this library is the CUDA path only\n");
@@ -250,7 +258,7 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
     }
     if (opt.loc != RNNT_GPU) return RNNT_STATUS_INVALID_VALUE;  // :90-92
     const uint64_t rows64 = (uint64_t)N * opt.maxT * opt.maxU;
-    if (rows64 >= (1ull << 31) || opt.maxU > 1024 * 1024 || opt.blank_label < 0 || opt.blank_label >= V)
+    if (rows64 >= (1ull << 31) || opt.blank_label < 0 || opt.blank_label >= V)
         return RNNT_STATUS_INVALID_VALUE;
     if (opt.maxU > 1024) {
         fprintf(stderr, "b200-rnnt: maxU > 1024 is not supported (the reference launches maxU threads per block and has the same limit)\n");
@@ -295,14 +303,14 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
 
     profile_begin_call();
     mark(0, s);
-    // pass 1: log-softmax statistics + (blank, label) log-prob gather
-    stream_pass<T>(acts, nullptr, labels, xlen, ylen, w, scale, d, s, 1);
-    mark(1, s);
+    if (phase != kBackward) {
+        // pass 1: log-softmax statistics + (blank, label) log-prob gather
+        stream_pass<T>(acts, nullptr, labels, xlen, ylen, w, scale, scale_vec, d, s, 1);
+        mark(1, s);
 
-    // lattice: alpha (and beta when gradients are wanted), one CTA per (utterance, direction)
-    {
+        // lattice: alpha (and beta when gradients are or will be wanted), one CTA per (utterance, direction)
         const int threads = (opt.maxU + 31) / 32 * 32;
-        dim3 grid(N, grads ? 2 : 1);
+        dim3 grid(N, (grads || want_beta) ? 2 : 1);
         T* cdev = async ? costs : static_cast<T*>(w.costs);
         const size_t ring = (size_t)kRing * threads * sizeof(typename Real<T>::pair);
         auto launch = [&](auto kernel) {
@@ -317,12 +325,15 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
         if (threads > 32) launch(lattice_kernel<T, true>);
         else launch(lattice_kernel<T, false>);
         ++g_last_launches;
+        mark(2, s);
+    } else {
+        mark(1, s);
+        mark(2, s);
     }
-    mark(2, s);
 
     // pass 2: dense gradient (+ zeros on padding)
-    if (grads) {
-        stream_pass<T>(acts, grads, labels, xlen, ylen, w, scale, d, s, 2);
+    if (grads && phase != kForward) {
+        stream_pass<T>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, 2);
         mark(3, s);
     }
 
@@ -359,7 +370,7 @@ rnntStatus_t compute_rnnt_loss(const float* const activations, float* gradients,
                                const int* const input_lengths, int alphabet_size, int minibatch,
                                float* costs, void* workspace, rnntOptions options) {
     return run<float>(activations, gradients, flat_labels, label_lengths, input_lengths,
-                      alphabet_size, minibatch, costs, false, 1.0f, workspace, options);
+                      alphabet_size, minibatch, costs, false, 1.0f, nullptr, kFull, false, workspace, options);
 }
 
 rnntStatus_t compute_rnnt_loss_fp64(const double* const activations, double* gradients,
@@ -369,7 +380,7 @@ rnntStatus_t compute_rnnt_loss_fp64(const double* const activations, double* gra
                                     int minibatch, double* costs, void* workspace,
                                     rnntOptions options) {
     return run<double>(activations, gradients, flat_labels, label_lengths, input_lengths,
-                       alphabet_size, minibatch, costs, false, 1.0, workspace, options);
+                       alphabet_size, minibatch, costs, false, 1.0, nullptr, kFull, false, workspace, options);
 }
 
 rnntStatus_t compute_rnnt_loss_async(const float* const activations, float* gradients,
@@ -379,7 +390,7 @@ rnntStatus_t compute_rnnt_loss_async(const float* const activations, float* grad
                                      int minibatch, float* costs_device, float grad_scale,
                                      void* workspace, rnntOptions options) {
     return run<float>(activations, gradients, flat_labels, label_lengths, input_lengths,
-                      alphabet_size, minibatch, costs_device, true, grad_scale, workspace, options);
+                      alphabet_size, minibatch, costs_device, true, grad_scale, nullptr, kFull, false, workspace, options);
 }
 
 rnntStatus_t compute_rnnt_loss_async_fp64(const double* const activations, double* gradients,
@@ -389,7 +400,45 @@ rnntStatus_t compute_rnnt_loss_async_fp64(const double* const activations, doubl
                                           int minibatch, double* costs_device, double grad_scale,
                                           void* workspace, rnntOptions options) {
     return run<double>(activations, gradients, flat_labels, label_lengths, input_lengths,
-                       alphabet_size, minibatch, costs_device, true, grad_scale, workspace, options);
+                       alphabet_size, minibatch, costs_device, true, grad_scale, nullptr, kFull, false, workspace, options);
+}
+
+rnntStatus_t rnnt_b200_forward(const float* const activations, const int* const flat_labels,
+                               const int* const label_lengths, const int* const input_lengths,
+                               int alphabet_size, int minibatch, float* costs_device,
+                               int prepare_backward, void* workspace, rnntOptions options) {
+    return run<float>(activations, nullptr, flat_labels, label_lengths, input_lengths, alphabet_size,
+                      minibatch, costs_device, true, 1.0f, nullptr, kForward, prepare_backward != 0,
+                      workspace, options);
+}
+
+rnntStatus_t rnnt_b200_forward_fp64(const double* const activations, const int* const flat_labels,
+                                    const int* const label_lengths, const int* const input_lengths,
+                                    int alphabet_size, int minibatch, double* costs_device,
+                                    int prepare_backward, void* workspace, rnntOptions options) {
+    return run<double>(activations, nullptr, flat_labels, label_lengths, input_lengths, alphabet_size,
+                       minibatch, costs_device, true, 1.0, nullptr, kForward, prepare_backward != 0,
+                       workspace, options);
+}
+
+rnntStatus_t rnnt_b200_backward(const float* const activations, float* gradients,
+                                const int* const flat_labels, const int* const label_lengths,
+                                const int* const input_lengths, int alphabet_size, int minibatch,
+                                const float* grad_costs_device, float grad_scale, void* workspace,
+                                rnntOptions options) {
+    return run<float>(activations, gradients, flat_labels, label_lengths, input_lengths, alphabet_size,
+                      minibatch, nullptr, true, grad_scale, grad_costs_device, kBackward, false,
+                      workspace, options);
+}
+
+rnntStatus_t rnnt_b200_backward_fp64(const double* const activations, double* gradients,
+                                     const int* const flat_labels, const int* const label_lengths,
+                                     const int* const input_lengths, int alphabet_size,
+                                     int minibatch, const double* grad_costs_device,
+                                     double grad_scale, void* workspace, rnntOptions options) {
+    return run<double>(activations, gradients, flat_labels, label_lengths, input_lengths,
+                       alphabet_size, minibatch, nullptr, true, grad_scale, grad_costs_device,
+                       kBackward, false, workspace, options);
 }
 
 rnntStatus_t get_workspace_size(int maxT, int maxU, int minibatch, bool gpu, size_t* size_bytes,

@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(kRowThreads, RNNT_GRAD_MINB)
 grad_row_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
                 const int* __restrict__ xlen, const int* __restrict__ ylen,
                 const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
-                const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
+                const double* __restrict__ betas, const double* __restrict__ llf, const T scale_in,
+                const T* __restrict__ scale_vec,
                 const Dims d) {
     const uint32_t r = d.rows - 1 - blockIdx.x;
     uint32_t bt, u, b, t;
@@ -478,6 +479,8 @@ grad_row_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __
     const int kb = d.blank;
     const T* row = acts + (uint64_t)r * d.V;
     T* grow = grads + (uint64_t)r * d.V;
+    // per-utterance upstream gradient (autograd's grad_output) times the scalar factor
+    const T scale = (SCALED && scale_vec) ? __ldg(scale_vec + b) * scale_in : scale_in;
     if ((int)t >= Tb || (int)u >= Ub) {
         VecT<T, VEC> z;
 #pragma unroll
@@ -517,7 +520,8 @@ __global__ void __launch_bounds__(256)
 grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
                  const int* __restrict__ xlen, const int* __restrict__ ylen,
                  const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
-                 const double* __restrict__ betas, const double* __restrict__ llf, const T scale,
+                 const double* __restrict__ betas, const double* __restrict__ llf, const T scale_in,
+                const T* __restrict__ scale_vec,
                  const Dims d) {
     constexpr int RPW = kWarp / LPR;
     const int lane = threadIdx.x & 31;
@@ -537,6 +541,7 @@ grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* _
         utt_extent(d, xlen, ylen, b, Tb, Ub);
         const T* row = acts + (uint64_t)r * d.V;
         T* grow = grads + (uint64_t)r * d.V;
+        const T scale = (SCALED && scale_vec) ? __ldg(scale_vec + b) * scale_in : scale_in;
         if ((int)t >= Tb || (int)u >= Ub) {
             VecT<T, VEC> z;
 #pragma unroll

@@ -5,20 +5,26 @@ Same public surface as the reference package (pytorch_binding/warprnnt_pytorch/_
 blank=0, reduction='mean')`` and the ``warp_rnnt`` extension functions, with the reference's
 input rules and error types (certify_inputs, :115-140).  Differences, all on the fast side:
 the call never synchronises with the host except for the reference's own length check, costs
-stay on the device, no zeros_like / mul_ passes over the [N,T,U,V] gradient (the kernel writes
-every element, already scaled for 'mean').  CPU tensors are rejected: there is no host path.
+stay on the device, and the gradient is produced in autograd's backward with grad_output and the
+'mean' factor folded into the kernel - no zeros_like / mul_ passes over the [N,T,U,V] tensor.
+CPU tensors are rejected: there is no host path.
 """
 import torch
 from torch.autograd import Function
 from torch.nn import Module
 
 from . import warp_rnnt
-from .warp_rnnt import cpu_rnnt, gpu_rnnt, gpu_rnnt_async  # noqa: F401
+from .warp_rnnt import cpu_rnnt, gpu_rnnt, gpu_rnnt_async, gpu_rnnt_backward, gpu_rnnt_forward  # noqa: F401
 
 __all__ = ['rnnt_loss', 'RNNTLoss']
 
 
 class _RNNT(Function):
+    """One training step costs the algorithmic 12 B per logit: forward() reads the logits once
+    (statistics + alpha/beta lattices, 4 B), backward() reads them again and writes the gradient
+    with the upstream gradient and the 'mean' factor already applied (8 B).  The reference makes
+    four more full-tensor passes around its C call (zeros_like, memset, grads /= N, grads.mul_)."""
+
     @staticmethod
     def forward(ctx, acts, labels, act_lens, label_lens, blank, reduction):
         """
@@ -34,24 +40,32 @@ class _RNNT(Function):
             raise ValueError("reduction must be 'none', 'sum' or 'mean'")
         minibatch_size = acts.size(0)
         need_grad = acts.requires_grad
-        grads = torch.empty_like(acts) if need_grad else None   # kernel defines every element
         costs = torch.empty(minibatch_size, dtype=acts.dtype, device=acts.device)
-        # reference :38-40 divides costs and grads by N for 'mean'; the scale rides in the kernel
-        scale = 1.0 / minibatch_size if reduction == 'mean' else 1.0
-        ws = gpu_rnnt_async(acts, labels, act_lens, label_lens, costs, grads, blank, scale)
-        ctx.workspace = ws
+        ws = warp_rnnt.gpu_rnnt_forward(acts, labels, act_lens, label_lens, costs, blank,
+                                        prepare_backward=need_grad)
+        if need_grad:
+            ctx.save_for_backward(acts, labels, act_lens, label_lens)
+            ctx.workspace = ws
+            ctx.blank = blank
+            # reference :38-40 divides costs and grads by N for 'mean'
+            ctx.scale = 1.0 / minibatch_size if reduction == 'mean' else 1.0
         if reduction in ('sum', 'mean'):
             costs = costs.sum().unsqueeze_(-1)
             if reduction == 'mean':
                 costs /= minibatch_size
-        ctx.grads = grads
         return costs
 
     @staticmethod
     def backward(ctx, grad_output):
-        # reference :47-50
-        grad_output = grad_output.view(-1, 1, 1, 1).to(ctx.grads)
-        return ctx.grads.mul_(grad_output), None, None, None, None, None
+        # reference :47-50: grads.mul_(grad_output.view(-1,1,1,1)); here the factor rides in the kernel
+        acts, labels, act_lens, label_lens = ctx.saved_tensors
+        n = acts.size(0)
+        g = grad_output.reshape(-1).to(device=acts.device, dtype=acts.dtype)
+        g = g.expand(n).contiguous() if g.numel() == 1 else g.contiguous()
+        grads = torch.empty_like(acts)   # the kernel defines every element (zeros on padding)
+        warp_rnnt.gpu_rnnt_backward(acts, labels, act_lens, label_lens, grads, g, ctx.blank,
+                                    ctx.scale, ctx.workspace)
+        return grads, None, None, None, None, None
 
 
 def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction='mean'):

@@ -42,6 +42,14 @@ _lib.compute_rnnt_loss_async.restype = C.c_int
 _lib.compute_rnnt_loss_async.argtypes = [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P, rnntOptions]
 _lib.compute_rnnt_loss_async_fp64.restype = C.c_int
 _lib.compute_rnnt_loss_async_fp64.argtypes = [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_double, _P, rnntOptions]
+for _name, _ct in (("rnnt_b200_forward", C.c_float), ("rnnt_b200_forward_fp64", C.c_double)):
+    _f = getattr(_lib, _name)
+    _f.restype = C.c_int
+    _f.argtypes = [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, rnntOptions]
+for _name, _ct in (("rnnt_b200_backward", C.c_float), ("rnnt_b200_backward_fp64", C.c_double)):
+    _f = getattr(_lib, _name)
+    _f.restype = C.c_int
+    _f.argtypes = [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _ct, _P, rnntOptions]
 _lib.get_workspace_size.restype = C.c_int
 _lib.get_workspace_size.argtypes = [C.c_int, C.c_int, C.c_int, C.c_bool, C.POINTER(C.c_size_t), C.c_size_t]
 _lib.get_warprnnt_version.restype = C.c_int
@@ -158,6 +166,47 @@ def gpu_rnnt_async(acts, labels, input_lengths, label_lengths, costs, grads, bla
     if st != RNNT_STATUS_SUCCESS:
         raise RuntimeError("compute_rnnt_loss_async failed: " + status_string(st))
     return workspace
+
+
+def _pick(acts, f32, f64):
+    if acts.dtype == torch.float32:
+        return getattr(_lib, f32), 4
+    if acts.dtype == torch.float64:
+        return getattr(_lib, f64), 8
+    raise TypeError("unsupported data type %s" % acts.dtype)
+
+
+def gpu_rnnt_forward(acts, labels, input_lengths, label_lengths, costs, blank_label,
+                     prepare_backward=True, workspace=None):
+    """Training-step split, first half: statistics + lattices into `workspace`, costs on the
+    device, no synchronisation.  Returns the workspace tensor (hand it to gpu_rnnt_backward)."""
+    N, T, U, V = acts.shape
+    fn, esz = _pick(acts, "rnnt_b200_forward", "rnnt_b200_forward_fp64")
+    with torch.cuda.device(acts.device):
+        need = workspace_size(T, U, N, esz)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=acts.device)
+        st = fn(acts.data_ptr(), _labels_ptr(labels), label_lengths.data_ptr(), input_lengths.data_ptr(),
+                V, N, costs.data_ptr(), 1 if prepare_backward else 0, workspace.data_ptr(),
+                _options(acts, blank_label))
+    if st != RNNT_STATUS_SUCCESS:
+        raise RuntimeError("rnnt_b200_forward failed: " + status_string(st))
+    return workspace
+
+
+def gpu_rnnt_backward(acts, labels, input_lengths, label_lengths, grads, grad_costs, blank_label,
+                      grad_scale, workspace):
+    """Second half: grads[b] = grad_scale * grad_costs[b] * d cost[b] / d acts[b] from the lattices
+    gpu_rnnt_forward left in `workspace` (grad_costs: device tensor [N] or None for ones)."""
+    N, T, U, V = acts.shape
+    fn, esz = _pick(acts, "rnnt_b200_backward", "rnnt_b200_backward_fp64")
+    with torch.cuda.device(acts.device):
+        st = fn(acts.data_ptr(), grads.data_ptr(), _labels_ptr(labels), label_lengths.data_ptr(),
+                input_lengths.data_ptr(), V, N, _ptr(grad_costs), grad_scale, workspace.data_ptr(),
+                _options(acts, blank_label))
+    if st != RNNT_STATUS_SUCCESS:
+        raise RuntimeError("rnnt_b200_backward failed: " + status_string(st))
+    return 0
 
 
 def profile_collect():
