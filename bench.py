@@ -253,7 +253,7 @@ def run_b200_arm(args):
     def step():
         wr.gpu_rnnt_async(acts, labels, tl, ul, costs, grads, 0, 1.0, ws)
         torch.sum(costs, 0, keepdim=True, out=loss)
-        if world > 1:
+        if world > 1 and not os.environ.get("BENCH_NO_ALLREDUCE"):
             dist.all_reduce(loss)      # the path's only exchange: one scalar over NVLink
 
     wr.set_profiling(True)
@@ -326,7 +326,14 @@ def run_b200_arm(args):
     e2e_ms = f0.elapsed_time(f1)
     clocks = sampler.result()
 
+    per_rank = None
     if world > 1:
+        # diagnostics: every rank's own kernel times and loop time (gathered, not used for `value`)
+        mine = torch.tensor([total_ms, kms[0] / args.steps, kms[1] / args.steps, kms[2] / args.steps],
+                            device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(v), 4) for v in r.tolist()] for r in allr]
         t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = t.tolist()
@@ -372,6 +379,8 @@ def run_b200_arm(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "lib": os.path.relpath(wr.lib_path(), ROOT),
         }
+        if per_rank is not None:
+            line["per_rank_ms"] = {"columns": ["loop_total", "rowstats", "lattice", "grad"], "rows": per_rank}
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

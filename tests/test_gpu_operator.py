@@ -166,3 +166,30 @@ def test_forward_backward_split_matches_full_call():
     wr.gpu_rnnt_backward(acts, labels, tl, ul, g_split, w, 0, 0.25, ws)
     torch.cuda.synchronize()
     assert torch.allclose(g_split, g_full * (0.25 * w).view(-1, 1, 1, 1), rtol=1e-6, atol=0)
+
+
+def test_async_entry_is_cuda_graph_capturable():
+    """compute_rnnt_loss_async makes no allocation, no synchronisation and no host round trip, so a
+    training step's loss can be captured into a CUDA graph and replayed on new data."""
+    from warprnnt_pytorch import warp_rnnt as wr
+    rng = np.random.default_rng(8)
+    N, T, U, V = 4, 12, 5, 28
+    acts = torch.tensor(rng.standard_normal((N, T, U, V)).astype(np.float32), device="cuda")
+    labels_np = rng.integers(1, V, size=(N, U - 1)).astype(np.int32)
+    labels = torch.as_tensor(labels_np).cuda()
+    tl_np, ul_np = np.full(N, T, np.int32), np.full(N, U - 1, np.int32)
+    tl, ul = torch.as_tensor(tl_np).cuda(), torch.as_tensor(ul_np).cuda()
+    costs, grads = torch.empty(N, device="cuda"), torch.empty_like(acts)
+    ws = torch.empty(wr.workspace_size(T, U, N, 4), dtype=torch.uint8, device="cuda")
+    wr.gpu_rnnt_async(acts, labels, tl, ul, costs, grads, 0, 1.0, ws)      # warm-up outside capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        wr.gpu_rnnt_async(acts, labels, tl, ul, costs, grads, 0, 1.0, ws)
+    new = rng.standard_normal((N, T, U, V)).astype(np.float32)
+    acts.copy_(torch.tensor(new))
+    g.replay()
+    torch.cuda.synchronize()
+    c_ref, g_ref, _ = pyoracle.rnnt_logits(new.astype(np.float64), labels_np, tl_np, ul_np, 0)
+    assert np.allclose(costs.cpu().numpy(), c_ref, rtol=1e-5)
+    assert np.allclose(grads.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)
