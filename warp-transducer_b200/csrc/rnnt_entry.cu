@@ -58,6 +58,36 @@ inline int read_set(EventSet& es, float* ms3) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Side streams for overlapping the (latency-bound, few-SM) lattice kernel of one group of
+// utterances with the (bandwidth-bound) streaming passes of the others.  High priority so the
+// lattice CTAs are placed as soon as short-lived streaming CTAs retire.  Fork/join with events on
+// the caller's stream only, so the call stays capturable and stream-ordered for the caller.
+constexpr int kMaxGroups = 4;
+struct SidePool {
+    cudaStream_t stream[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t forked[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t joined[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+    int device = -1;
+    bool ok = false;
+};
+SidePool& side_pool() {
+    thread_local SidePool pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pool.device != dev) {  // first use on this thread/device (pools of other devices are leaked, tiny)
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        pool.ok = true;
+        for (int g = 0; g < kMaxGroups; ++g) {
+            pool.ok &= cudaStreamCreateWithPriority(&pool.stream[g], cudaStreamNonBlocking, hi) == cudaSuccess;
+            pool.ok &= cudaEventCreateWithFlags(&pool.forked[g], cudaEventDisableTiming) == cudaSuccess;
+            pool.ok &= cudaEventCreateWithFlags(&pool.joined[g], cudaEventDisableTiming) == cudaSuccess;
+        }
+        pool.device = dev;
+    }
+    return pool;
+}
+
 // ---- workspace carve-up (all sections 256-B aligned) -------------------------------------------
 struct Workspace {
     void* stat;     // pair<T>  [rows]   (row max, log sum exp)
@@ -301,40 +331,123 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
         }
     }
 
-    profile_begin_call();
-    mark(0, s);
-    if (phase != kBackward) {
-        // pass 1: log-softmax statistics + (blank, label) log-prob gather
-        stream_pass<T>(acts, nullptr, labels, xlen, ylen, w, scale, scale_vec, d, s, 1);
-        mark(1, s);
-
-        // lattice: alpha (and beta when gradients are or will be wanted), one CTA per (utterance, direction)
+    // ---- batch groups: utterances are independent, every array is batch-major, so a group is the
+    // same problem on offset pointers.  One group = the plain in-order pipeline.
+    const size_t cell_stride = (size_t)opt.maxT * opt.maxU;            // rows per utterance
+    const size_t lat_stride = (size_t)(opt.maxT + opt.maxU - 1) * opt.maxU;
+    const size_t lab_stride = opt.maxU > 1 ? opt.maxU - 1 : 0;
+    using Pair = typename Real<T>::pair;
+    T* cdev = async ? costs : static_cast<T*>(w.costs);
+    struct Group {
+        Workspace w;
+        Dims d;
+        const T* acts;
+        T* grads;
+        const int *labels, *xlen, *ylen;
+        T* costs;
+        const T* scale_vec;
+    };
+    auto make_group = [&](int b0, int nb) {
+        Group g;
+        g.w = w;
+        g.w.stat = static_cast<Pair*>(w.stat) + (size_t)b0 * cell_stride;
+        g.w.lp2 = static_cast<Pair*>(w.lp2) + (size_t)b0 * lat_stride;
+        g.w.alphas = w.alphas + (size_t)b0 * lat_stride;
+        g.w.betas = w.betas + (size_t)b0 * lat_stride;
+        g.w.llf = w.llf + b0;
+        g.w.llb = w.llb + b0;
+        g.d = d;
+        g.d.N = nb;
+        g.d.rows = (uint32_t)((size_t)nb * cell_stride);
+        g.acts = acts + (size_t)b0 * cell_stride * V;
+        g.grads = grads ? grads + (size_t)b0 * cell_stride * V : nullptr;
+        g.labels = labels + (size_t)b0 * lab_stride;
+        g.xlen = xlen + b0;
+        g.ylen = ylen + b0;
+        g.costs = cdev ? cdev + b0 : nullptr;
+        g.scale_vec = scale_vec ? scale_vec + b0 : nullptr;
+        return g;
+    };
+    const bool with_beta = grads || want_beta;
+    auto launch_lattice = [&](const Group& g, cudaStream_t st) {
         const int threads = (opt.maxU + 31) / 32 * 32;
-        dim3 grid(N, (grads || want_beta) ? 2 : 1);
-        T* cdev = async ? costs : static_cast<T*>(w.costs);
-        const size_t ring = (size_t)kRing * threads * sizeof(typename Real<T>::pair);
+        dim3 grid(g.d.N, with_beta ? 2 : 1);
+        const size_t ring = (size_t)kRing * threads * sizeof(Pair);
         auto launch = [&](auto kernel) {
             static thread_local size_t opted = 0;
             if (ring > 48 * 1024 && ring > opted) {
                 cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
                 opted = ring;
             }
-            kernel<<<grid, threads, ring, s>>>(static_cast<const typename Real<T>::pair*>(w.lp2), xlen,
-                                              ylen, w.alphas, w.betas, w.llf, w.llb, cdev, d);
+            kernel<<<grid, threads, ring, st>>>(static_cast<const Pair*>(g.w.lp2), g.xlen, g.ylen,
+                                               g.w.alphas, g.w.betas, g.w.llf, g.w.llb, g.costs, g.d);
         };
         if (threads > 32) launch(lattice_kernel<T, true>);
         else launch(lattice_kernel<T, false>);
         ++g_last_launches;
-        mark(2, s);
-    } else {
-        mark(1, s);
-        mark(2, s);
+    };
+
+    // Overlap decision: the wavefront costs ~0.25 us per anti-diagonal whatever the batch; the
+    // streaming passes cost 12 B/elt at ~6.9 TB/s.  Worth splitting only when the lattice is a
+    // visible share of a call that is long enough to amortise the extra launches.
+    // Measured on B200 (N=64,T=1500,U=301,V=50): 3.88 -> 3.77 ms with 4 groups; the co-running
+    // lattice CTAs slow the streaming kernels a little, so the gain is modest, and there is none
+    // when no pass 2 follows in the same call (loss-only / operator forward) - those stay in order.
+    int groups = 1;
+    if (phase == kFull && grads && N >= 2 * kMaxGroups) {
+        static const int forced = [] { const char* e = getenv("RNNT_B200_GROUPS"); return e ? atoi(e) : 0; }();
+        const double lattice_us = 0.25 * (opt.maxT + opt.maxU) + 20.0;
+        const double stream_us = (double)rows64 * V * sizeof(T) * (grads ? 3.0 : 1.0) / 6.9e6;
+        if (stream_us > 400.0 && lattice_us > 0.08 * stream_us) groups = kMaxGroups;
+        if (forced >= 1 && forced <= kMaxGroups) groups = forced;
+        if (groups > 1 && !side_pool().ok) groups = 1;
     }
 
-    // pass 2: dense gradient (+ zeros on padding)
-    if (grads && phase != kForward) {
-        stream_pass<T>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, 2);
-        mark(3, s);
+    profile_begin_call();
+    mark(0, s);
+    if (groups == 1) {
+        const Group g = make_group(0, N);
+        if (phase != kBackward) {
+            // pass 1: log-softmax statistics + (blank, label) log-prob gather
+            stream_pass<T>(g.acts, nullptr, g.labels, g.xlen, g.ylen, g.w, scale, g.scale_vec, g.d, s, 1);
+            mark(1, s);
+            // lattice: alpha (and beta when gradients are or will be wanted)
+            launch_lattice(g, s);
+        } else {
+            mark(1, s);
+        }
+        mark(2, s);
+        // pass 2: dense gradient (+ zeros on padding)
+        if (grads && phase != kForward) {
+            stream_pass<T>(g.acts, g.grads, g.labels, g.xlen, g.ylen, g.w, scale, g.scale_vec, g.d, s, 2);
+            mark(3, s);
+        }
+    } else {
+        SidePool& pool = side_pool();
+        Group gs[kMaxGroups];
+        for (int k = 0; k < groups; ++k) {
+            const int b0 = (int)((int64_t)N * k / groups), b1 = (int)((int64_t)N * (k + 1) / groups);
+            gs[k] = make_group(b0, b1 - b0);
+        }
+        // main stream: pass 1 of every group back to back; each group's lattice forks off behind it
+        for (int k = 0; k < groups; ++k) {
+            stream_pass<T>(gs[k].acts, nullptr, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w, scale,
+                           gs[k].scale_vec, gs[k].d, s, 1);
+            cudaEventRecord(pool.forked[k], s);
+            cudaStreamWaitEvent(pool.stream[k], pool.forked[k], 0);
+            launch_lattice(gs[k], pool.stream[k]);
+            cudaEventRecord(pool.joined[k], pool.stream[k]);
+        }
+        mark(1, s);
+        // main stream: join each lattice, then that group's pass 2 (or just join, forward-only)
+        for (int k = 0; k < groups; ++k) {
+            cudaStreamWaitEvent(s, pool.joined[k], 0);
+            if (k == 0) mark(2, s);
+            if (grads && phase != kForward)
+                stream_pass<T>(gs[k].acts, gs[k].grads, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w,
+                               scale, gs[k].scale_vec, gs[k].d, s, 2);
+        }
+        if (grads && phase != kForward) mark(3, s);
     }
 
     if (cudaGetLastError() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
