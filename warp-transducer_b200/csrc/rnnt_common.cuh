@@ -57,6 +57,7 @@ template <> struct Real<float> {
         return y;
     }
     static __device__ __forceinline__ float log(float x) { return logf(x); }
+    static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }  // one FMNMX
     static constexpr float kLog2e = 1.4426950408889634f;
 };
 template <> struct Real<double> {
@@ -65,6 +66,7 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double exp2(double x) { return ::exp2(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
+    static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
     static constexpr double kLog2e = 1.4426950408889634;
 };
 
@@ -150,7 +152,7 @@ template <int LPR, typename T> __device__ __forceinline__ T group_max(T v) {
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) {
         T w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = w > v ? w : v;
+        v = Real<T>::max(v, w);
     }
     return v;
 }

@@ -91,7 +91,7 @@ rowstats_row_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
 #pragma unroll
         for (int j = 0; j < NV; ++j)
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) vm = x[j].v[c] > vm ? x[j].v[c] : vm;
+            for (int c = 0; c < VEC; ++c) vm = R::max(vm, x[j].v[c]);
         if (vm > m) {
             s *= R::exp(m - vm);
             m = vm;
@@ -185,7 +185,7 @@ rowstats_tile_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
 #pragma unroll
         for (int j = 0; j < kVPL; ++j)
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) m = x[j].v[c] > m ? x[j].v[c] : m;
+            for (int c = 0; c < VEC; ++c) m = R::max(m, x[j].v[c]);
         const T M = group_max<LPR>(m);
         const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
         T s = 0;
