@@ -193,3 +193,34 @@ def test_async_entry_is_cuda_graph_capturable():
     c_ref, g_ref, _ = pyoracle.rnnt_logits(new.astype(np.float64), labels_np, tl_np, ul_np, 0)
     assert np.allclose(costs.cpu().numpy(), c_ref, rtol=1e-5)
     assert np.allclose(grads.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)
+
+
+def test_native_extension_module_matches():
+    """warp-transducer_b200/binding/binding.cpp: the compiled (pybind11/libtorch) form of the
+    reference's `warp_rnnt` extension module, same call as the reference's _RNNT.forward makes."""
+    import importlib.util
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                      "warp-transducer_b200", "lib", "warp_rnnt_native.so")
+    if not os.path.exists(so):
+        pytest.skip("native binding not built")
+    spec = importlib.util.spec_from_file_location("warp_rnnt_native", so)
+    native = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(native)
+    rng = np.random.default_rng(11)
+    N, T, U, V = 3, 9, 4, 28
+    acts_np = rng.random((N, T, U, V)).astype(np.float32)
+    labels_np = rng.integers(1, V, size=(N, U - 1)).astype(np.int32)
+    tl_np = np.array([T, 6, 9], np.int32)
+    ul_np = np.array([U - 1, 2, 0], np.int32)
+    c_ref, g_ref, _ = pyoracle.rnnt_logits(acts_np.astype(np.float64), labels_np, tl_np, ul_np, 0)
+    for dt in (torch.float32, torch.float64):
+        acts = torch.tensor(acts_np, dtype=dt).cuda()
+        grads = torch.zeros_like(acts)
+        costs = torch.zeros(N, dtype=dt)
+        rc = native.gpu_rnnt(acts, *(torch.as_tensor(x).cuda() for x in (labels_np, tl_np, ul_np)), costs, grads, 0, 0)
+        assert rc == 0
+        assert np.allclose(costs.numpy(), c_ref, rtol=1e-5)
+        assert np.allclose(grads.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        native.cpu_rnnt(acts.cpu(), acts.cpu(), acts.cpu(), acts.cpu(), costs, grads.cpu(), 0, 0)
