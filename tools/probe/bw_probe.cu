@@ -117,6 +117,45 @@ __global__ void __launch_bounds__(256) read_rows_warp(const float* __restrict__ 
     if (acc == 123.456f) *sink = acc;
 }
 
+// CTA per row through TMA bulk copies: global -> smem (mbarrier complete_tx), compute in place,
+// smem -> global (bulk_group).  SASS: UBLKCP.  Rows must be 16-B multiples.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int MATH>
+__global__ void __launch_bounds__(256) row_tma(const float* __restrict__ in, float* __restrict__ out, int rows, int V) {
+    extern __shared__ __align__(128) float buf[];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned r = rows - 1 - blockIdx.x;
+    const unsigned bytes = V * 4;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(buf)), "l"(in + (size_t)r * V), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    }
+    float4* b4 = reinterpret_cast<float4*>(buf);
+    for (int i = threadIdx.x; i < V / 4; i += 256) {
+        float4 g = b4[i];
+        if (MATH) { g.x = exp2f(g.x * 1.44f - 3.f); g.y = exp2f(g.y * 1.44f - 3.f); g.z = exp2f(g.z * 1.44f - 3.f); g.w = exp2f(g.w * 1.44f - 3.f); }
+        b4[i] = g;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (size_t)r * V), "r"(smem_u32(buf)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
 int main() {
     const int rows = 128 * 150 * 21, V = 5000;
     const size_t n = (size_t)rows * V, n4 = n / 4;
@@ -158,5 +197,11 @@ int main() {
     time("read_row_cta non-persistent", [&] { read_row_cta<5><<<rows, 256>>>(a, b, rows, V); });
     time("read_rows_warp UNR4 persistent 6 blk/SM", [&] { read_rows_warp<4><<<sms * 6, 256>>>(a, b, rows, V); });
     time("read_rows_warp UNR4 non-persistent", [&] { read_rows_warp<4><<<rows / 8, 256>>>(a, b, rows, V); });
+    printf("TMA bulk (cp.async.bulk, CTA per row, in-place compute in smem):\n");
+    cudaFuncSetAttribute(row_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, V * 4);
+    cudaFuncSetAttribute(row_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, V * 4);
+    time("row_tma copy", [&] { row_tma<0><<<rows, 256, V * 4>>>(a, b, rows, V); });
+    time("row_tma exp", [&] { row_tma<1><<<rows, 256, V * 4>>>(a, b, rows, V); });
+    { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) printf("row_tma error: %s\n", cudaGetErrorString(e)); }
     return 0;
 }
