@@ -317,3 +317,24 @@ def test_full_config4_long_utterance(wr):     # N=64,T=1500,L=300,A=50
 
 def test_full_config5_one_gpu_shard(wr):      # N=1024/8 per GPU, T=200,L=40,A=5000
     _full_shape_properties(wr, 128, 200, 40, 5000, check_utts=(1,))
+
+
+def test_fuzz_random_shapes_against_oracle(wr):
+    """Seeded sweep over awkward shapes (odd vocabularies around every dispatch boundary, U around
+    the warp size, ragged lengths, random blank) - each checked against the fp64 oracle."""
+    rng = np.random.default_rng(2026)
+    vocab = [2, 3, 7, 8, 9, 15, 16, 17, 31, 33, 63, 64, 65, 127, 129, 255, 256, 257, 260, 511, 513,
+             1023, 1025, 2047, 2052]
+    for case in range(40):
+        V = int(rng.choice(vocab))
+        N = int(rng.integers(1, 5))
+        T = int(rng.integers(1, 24))
+        U = int(rng.choice([1, 2, 3, 5, 31, 32, 33, 34, 64, 65]))
+        if T * U * V > 400000:
+            T = max(1, 400000 // (U * V))
+        blank = int(rng.integers(0, V))
+        acts, labels, tl, ul = make_inputs(1000 + case, N, T, U, V, blank,
+                                           dist="normal" if case % 2 else "uniform")
+        c_ref, g_ref, _ = pyoracle.rnnt_logits(acts.astype(np.float64), labels, tl, ul, blank)
+        costs, g = call_abi(wr, acts, labels, tl, ul, blank)
+        check_against(costs, g, c_ref, g_ref, "fuzz %d: N%d T%d U%d V%d blank%d" % (case, N, T, U, V, blank))
