@@ -180,6 +180,28 @@ rnntStatus_t rnnt_b200_backward_fp64(const double* const activations, double* gr
                                      int minibatch, const double* grad_costs_device,
                                      double grad_scale, void* workspace, struct rnntOptions options);
 
+/*
+ * 16-bit storage variants: logits and gradients in bf16 or fp16, arithmetic,
+ * lattice and costs in fp32; 6 B per logit instead of 12.  Same semantics as the async / split
+ * entries above; workspace sized with dtype_size = sizeof(float).  dtype: RNNT_B200_BF16 / _FP16.
+ * The 16-B fast path needs alphabet_size % 8 == 0 and 16-B aligned tensors (else element-wise).
+ */
+enum { RNNT_B200_BF16 = 1, RNNT_B200_FP16 = 2 };
+rnntStatus_t rnnt_b200_loss_async_16(int dtype, const void* activations, void* gradients,
+                                     const int* flat_labels, const int* label_lengths,
+                                     const int* input_lengths, int alphabet_size, int minibatch,
+                                     float* costs_device, float grad_scale, void* workspace,
+                                     struct rnntOptions options);
+rnntStatus_t rnnt_b200_forward_16(int dtype, const void* activations, const int* flat_labels,
+                                  const int* label_lengths, const int* input_lengths,
+                                  int alphabet_size, int minibatch, float* costs_device,
+                                  int prepare_backward, void* workspace, struct rnntOptions options);
+rnntStatus_t rnnt_b200_backward_16(int dtype, const void* activations, void* gradients,
+                                   const int* flat_labels, const int* label_lengths,
+                                   const int* input_lengths, int alphabet_size, int minibatch,
+                                   const float* grad_costs_device, float grad_scale, void* workspace,
+                                   struct rnntOptions options);
+
 /* Number of kernels the last compute call on this thread launched (bench.py's gpu_launches). */
 int rnnt_b200_last_launch_count(void);
 

@@ -224,3 +224,35 @@ def test_native_extension_module_matches():
         assert np.allclose(grads.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)
     with pytest.raises(RuntimeError):
         native.cpu_rnnt(acts.cpu(), acts.cpu(), acts.cpu(), acts.cpu(), costs, grads.cpu(), 0, 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_sixteen_bit_storage(dtype):
+    """bf16 / fp16 logits and gradients: fp32 arithmetic inside, so the only error
+    against the fp64 oracle evaluated on the SAME rounded inputs is the rounding of the output."""
+    from warprnnt_pytorch import RNNTLoss, warp_rnnt as wr
+    rng = np.random.default_rng(13)
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    for (N, T, U, V) in [(3, 11, 5, 64), (2, 7, 4, 5000), (2, 6, 3, 37), (2, 9, 34, 16)]:
+        acts_t = torch.tensor(rng.standard_normal((N, T, U, V)).astype(np.float32)).to(dtype)
+        acts_np = acts_t.float().numpy()                      # the rounded logits the kernel sees
+        labels_np = rng.integers(1, V, size=(N, U - 1)).astype(np.int32)
+        tl_np = rng.integers(T // 2 + 1, T + 1, size=N).astype(np.int32)
+        ul_np = rng.integers(0, U, size=N).astype(np.int32)
+        tl_np[0], ul_np[0] = T, U - 1
+        c_ref, g_ref, _ = pyoracle.rnnt_logits(acts_np.astype(np.float64), labels_np, tl_np, ul_np, 0)
+        acts = acts_t.cuda().requires_grad_(True)
+        labels, tl, ul = (torch.as_tensor(x).cuda() for x in (labels_np, tl_np, ul_np))
+        out = RNNTLoss(reduction='none')(acts, labels, tl, ul)
+        assert out.dtype == torch.float32
+        out.sum().backward()
+        assert acts.grad.dtype == dtype
+        assert np.allclose(out.detach().cpu().numpy(), c_ref, rtol=1e-5)
+        g = acts.grad.float().cpu().numpy()
+        assert np.allclose(g, g_ref, rtol=2 * eps, atol=1e-6), np.abs(g - g_ref).max()
+        # full (non-split) entry as well
+        c2 = torch.empty(N, device="cuda")
+        g2 = torch.empty_like(acts)
+        wr.gpu_rnnt_async(acts.detach(), labels, tl, ul, c2, g2, 0)
+        torch.cuda.synchronize()
+        assert torch.equal(g2, acts.grad) and torch.equal(c2, out.detach())

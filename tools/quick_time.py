@@ -14,13 +14,17 @@ CFG = {"c2": (128, 150, 40, 28), "c3": (128, 150, 20, 5000), "c4": (64, 1500, 30
 
 
 def main():
+    dt = torch.float32
+    if "--bf16" in sys.argv:
+        sys.argv.remove("--bf16")
+        dt = torch.bfloat16
     names = sys.argv[1:] or ["c2", "c3", "c4", "c5"]
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name in names:
         N, T, L, V = CFG[name]
         U = L + 1
-        acts = torch.rand((N, T, U, V), device=dev)
+        acts = torch.rand((N, T, U, V), device=dev).to(dt)
         grads = torch.empty_like(acts)
         rng = np.random.default_rng(1)
         labels = torch.as_tensor(rng.integers(1, V, size=(N, L)).astype(np.int32)).to(dev)
@@ -44,7 +48,7 @@ def main():
                     km += np.array(wr.last_kernel_ms()) / 5
             t = float(np.median(ts[3:]))
             E = N * T * U * V
-            bytes_ = (12 if g is not None else 4) * E
+            bytes_ = (12 if g is not None else 4) * E * acts.element_size() // 4
             print("%s %-9s N=%d T=%d U=%d V=%d: %.3f ms  %.0f utt/s  %.0f GB/s (algorithmic %d B/elt)  cost[0]=%.3f  kernels(rowstats,lattice,grad)=%s" % (
                 name, mode, N, T, U, V, t, N / t * 1e3, bytes_ / t / 1e6, 12 if g is not None else 4,
                 costs[0].item(), np.round(km, 3)), flush=True)

@@ -1,5 +1,7 @@
 // rnnt_common.cuh — small device/host helpers shared by the sm_100a RNN-T kernels.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -108,6 +110,7 @@ template <> struct ExpSum<double> {
 //   st_stream : evict-first store (gradients are never re-read by this library)
 // ---------------------------------------------------------------------------------------------
 template <int BYTES> struct Pack;
+template <> struct Pack<2> { using type = unsigned short; };
 template <> struct Pack<4> { using type = int; };
 template <> struct Pack<8> { using type = int2; };
 template <> struct Pack<16> { using type = int4; };
@@ -116,32 +119,61 @@ template <typename T, int VEC> struct alignas(sizeof(T) * VEC) VecT {
     T v[VEC];
 };
 
-template <typename T, int VEC> __device__ __forceinline__ VecT<T, VEC> ld_keep(const T* p) {
-    using P = typename Pack<sizeof(T) * VEC>::type;
+// Storage (IO) type -> arithmetic type.  float/double compute in themselves; the 16-bit storage
+// types (bf16 / fp16 logits and gradients) compute in float.
+template <typename IO> struct ComputeOf { using type = IO; };
+template <> struct ComputeOf<__nv_bfloat16> { using type = float; };
+template <> struct ComputeOf<__half> { using type = float; };
+
+template <typename T, typename IO> __device__ __forceinline__ T to_compute(IO v) { return (T)v; }
+template <> __device__ __forceinline__ float to_compute<float, __nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_compute<float, __half>(__half v) { return __half2float(v); }
+template <typename IO, typename T> __device__ __forceinline__ IO from_compute(T v) { return (IO)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_compute<__nv_bfloat16, float>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_compute<__half, float>(float v) { return __float2half_rn(v); }
+
+// VEC storage elements -> VEC arithmetic values (identity when IO == T)
+template <typename T, int VEC, typename IO, typename P>
+__device__ __forceinline__ VecT<T, VEC> unpack(P raw) {
     union {
         P raw;
-        VecT<T, VEC> val;
+        VecT<IO, VEC> val;
+    } x;
+    x.raw = raw;
+    VecT<T, VEC> out;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) out.v[c] = to_compute<T, IO>(x.val.v[c]);
+    return out;
+}
+
+template <typename T, int VEC, typename IO> __device__ __forceinline__ VecT<T, VEC> ld_keep(const IO* p) {
+    using P = typename Pack<sizeof(IO) * VEC>::type;
+    return unpack<T, VEC, IO, P>(__ldg(reinterpret_cast<const P*>(p)));
+}
+template <typename T, int VEC, typename IO> __device__ __forceinline__ VecT<T, VEC> ld_stream(const IO* p) {
+    using P = typename Pack<sizeof(IO) * VEC>::type;
+    return unpack<T, VEC, IO, P>(__ldcs(reinterpret_cast<const P*>(p)));
+}
+template <typename T, int VEC, typename IO>
+__device__ __forceinline__ void st_stream(IO* p, const VecT<T, VEC>& v) {
+    using P = typename Pack<sizeof(IO) * VEC>::type;
+    union {
+        P raw;
+        VecT<IO, VEC> val;
+    } x;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) x.val.v[c] = from_compute<IO, T>(v.v[c]);
+    __stcs(reinterpret_cast<P*>(p), x.raw);
+}
+// one element through the read-only path
+template <typename T, typename IO> __device__ __forceinline__ T ld_scalar(const IO* p) {
+    using P = typename Pack<sizeof(IO)>::type;
+    union {
+        P raw;
+        IO val;
     } x;
     x.raw = __ldg(reinterpret_cast<const P*>(p));
-    return x.val;
-}
-template <typename T, int VEC> __device__ __forceinline__ VecT<T, VEC> ld_stream(const T* p) {
-    using P = typename Pack<sizeof(T) * VEC>::type;
-    union {
-        P raw;
-        VecT<T, VEC> val;
-    } x;
-    x.raw = __ldcs(reinterpret_cast<const P*>(p));
-    return x.val;
-}
-template <typename T, int VEC> __device__ __forceinline__ void st_stream(T* p, const VecT<T, VEC>& v) {
-    using P = typename Pack<sizeof(T) * VEC>::type;
-    union {
-        P raw;
-        VecT<T, VEC> val;
-    } x;
-    x.val = v;
-    __stcs(reinterpret_cast<P*>(p), x.raw);
+    return to_compute<T, IO>(x.val);
 }
 
 // ---------------------------------------------------------------------------------------------

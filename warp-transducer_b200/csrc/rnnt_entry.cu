@@ -154,41 +154,41 @@ bool is_device_pointer(const void* p) {
 // ---- streaming-kernel dispatch on (vector width, row length) -------------------------------------
 // Long rows: one CTA per row (grid = rows).  Short rows: register tiles, 32/LPR rows per warp.
 // Both grids are non-persistent on purpose (see rnnt_kernels.cuh).
-template <typename T, int VEC, int NV>
-void launch_rowstats_row(const T* acts, const int* labels, const int* xlen, const int* ylen,
+template <typename T, int VEC, int NV, typename IO>
+void launch_rowstats_row(const IO* acts, const int* labels, const int* xlen, const int* ylen,
                          const Workspace& w, const Dims& d, cudaStream_t s) {
-    rowstats_row_kernel<T, VEC, NV><<<d.rows, kRowThreads, 0, s>>>(
+    rowstats_row_kernel<T, VEC, NV, IO><<<d.rows, kRowThreads, 0, s>>>(
         acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
         static_cast<typename Real<T>::pair*>(w.lp2), d);
     ++g_last_launches;
 }
 
-template <typename T, int VEC, int NV>
-void launch_grad_row(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+template <typename T, int VEC, int NV, typename IO>
+void launch_grad_row(const IO* acts, IO* grads, const int* labels, const int* xlen, const int* ylen,
                      const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s) {
-    auto k = (scale != T(1) || scale_vec) ? grad_row_kernel<T, VEC, NV, true>
-                                          : grad_row_kernel<T, VEC, NV, false>;
+    auto k = (scale != T(1) || scale_vec) ? grad_row_kernel<T, VEC, NV, true, IO>
+                                          : grad_row_kernel<T, VEC, NV, false, IO>;
     k<<<d.rows, kRowThreads, 0, s>>>(acts, grads, labels, xlen, ylen,
                                       static_cast<const typename Real<T>::pair*>(w.stat), w.alphas,
                                       w.betas, w.llf, scale, scale_vec, d);
     ++g_last_launches;
 }
 
-template <typename T, int VEC, int LPR>
-void launch_rowstats_tile(const T* acts, const int* labels, const int* xlen, const int* ylen,
+template <typename T, int VEC, int LPR, typename IO>
+void launch_rowstats_tile(const IO* acts, const int* labels, const int* xlen, const int* ylen,
                           const Workspace& w, const Dims& d, cudaStream_t s) {
     const uint64_t warps = ((uint64_t)d.rows * LPR + 31) / 32;
-    rowstats_tile_kernel<T, VEC, LPR><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(
+    rowstats_tile_kernel<T, VEC, LPR, IO><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(
         acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
         static_cast<typename Real<T>::pair*>(w.lp2), d);
     ++g_last_launches;
 }
 
-template <typename T, int VEC, int LPR>
-void launch_grad_tile(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+template <typename T, int VEC, int LPR, typename IO>
+void launch_grad_tile(const IO* acts, IO* grads, const int* labels, const int* xlen, const int* ylen,
                       const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s) {
-    auto k = (scale != T(1) || scale_vec) ? grad_tile_kernel<T, VEC, LPR, true>
-                                          : grad_tile_kernel<T, VEC, LPR, false>;
+    auto k = (scale != T(1) || scale_vec) ? grad_tile_kernel<T, VEC, LPR, true, IO>
+                                          : grad_tile_kernel<T, VEC, LPR, false, IO>;
     const uint64_t warps = ((uint64_t)d.rows * LPR + 31) / 32;
     k<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(acts, grads, labels, xlen, ylen,
                                                   static_cast<const typename Real<T>::pair*>(w.stat),
@@ -209,18 +209,18 @@ inline int pick_lpr(int nv) {
     return lpr;
 }
 
-template <typename T, int VEC>
-void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+template <typename T, int VEC, typename IO>
+void stream_passes(const IO* acts, IO* grads, const int* labels, const int* xlen, const int* ylen,
                    const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s, int pass) {
     const int nv = d.V / VEC;
     if (nv > 32 * kVPL) {  // long rows: CTA per row; NV = vectors per thread per trip
         const int per_thread = (nv + kRowThreads - 1) / kRowThreads;
 #define B200_ROW(NVV)                                                                             \
     do {                                                                                          \
-        if (pass == 1) launch_rowstats_row<T, VEC, NVV>(acts, labels, xlen, ylen, w, d, s);       \
-        else launch_grad_row<T, VEC, NVV>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s);       \
+        if (pass == 1) launch_rowstats_row<T, VEC, NVV, IO>(acts, labels, xlen, ylen, w, d, s);       \
+        else launch_grad_row<T, VEC, NVV, IO>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s);       \
     } while (0)
-        if (sizeof(T) == 4 && VEC == 4) {  // the fp32 fast path gets an exact register count
+        if (sizeof(IO) == 4 && VEC == 4) {  // the fp32 fast path gets an exact register count
             switch (per_thread) {
                 case 1: B200_ROW(1); break;
                 case 2: B200_ROW(2); break;
@@ -240,8 +240,8 @@ void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, 
     }
 #define B200_TILE(L)                                                                              \
     case L:                                                                                       \
-        if (pass == 1) launch_rowstats_tile<T, VEC, L>(acts, labels, xlen, ylen, w, d, s);        \
-        else launch_grad_tile<T, VEC, L>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s);        \
+        if (pass == 1) launch_rowstats_tile<T, VEC, L, IO>(acts, labels, xlen, ylen, w, d, s);        \
+        else launch_grad_tile<T, VEC, L, IO>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s);        \
         break;
     switch (pick_lpr(nv)) {
         B200_TILE(2)
@@ -253,31 +253,32 @@ void stream_passes(const T* acts, T* grads, const int* labels, const int* xlen, 
 #undef B200_TILE
 }
 
-template <typename T>
-void stream_pass(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+template <typename T, typename IO>
+void stream_pass(const IO* acts, IO* grads, const int* labels, const int* xlen, const int* ylen,
                  const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s, int pass) {
-    // widest vector the row pitch and the base pointers allow
+    // widest vector the row pitch and the base pointers allow (16-B vectors on the fast path)
     const uintptr_t mis = reinterpret_cast<uintptr_t>(acts) | reinterpret_cast<uintptr_t>(grads) |
-                          ((uintptr_t)d.V * sizeof(T));
-    constexpr int kMaxVec = 16 / sizeof(T);
+                          ((uintptr_t)d.V * sizeof(IO));
+    constexpr int kMaxVec = 16 / sizeof(IO);
     if (mis % 16 == 0)
-        stream_passes<T, kMaxVec>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
-    else if (sizeof(T) == 4 && mis % 8 == 0)
-        stream_passes<T, (kMaxVec > 2 ? 2 : 1)>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
+        stream_passes<T, kMaxVec, IO>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
+    else if (sizeof(IO) == 4 && mis % 8 == 0)
+        stream_passes<T, (sizeof(IO) == 4 ? 2 : 1), IO>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
     else
-        stream_passes<T, 1>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
+        stream_passes<T, 1, IO>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass);
 }
 
-// ---- the path -----------------------------------------------------------------------------------
 // What a call does.  The reference API is FULL (stats -> lattice -> grad in one call); the
 // operator splits a training step into FORWARD (stats + both lattices, costs out) and BACKWARD
 // (gradient pass only, reading the lattices the forward left in the workspace).
 enum Phase { kFull = 0, kForward = 1, kBackward = 2 };
 
-template <typename T>
-rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, const int* xlen,
-                 int V, int N, T* costs, bool async, T scale, const T* scale_vec, Phase phase,
-                 bool want_beta, void* workspace, rnntOptions opt) {
+template <typename IO>
+rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, const int* xlen,
+                 int V, int N, typename ComputeOf<IO>::type* costs, bool async,
+                 typename ComputeOf<IO>::type scale, const typename ComputeOf<IO>::type* scale_vec,
+                 Phase phase, bool want_beta, void* workspace, rnntOptions opt) {
+    using T = typename ComputeOf<IO>::type;  // arithmetic type (float for the 16-bit storage types)
     if (acts == nullptr || labels == nullptr || ylen == nullptr || xlen == nullptr ||
         (costs == nullptr && phase != kBackward) || workspace == nullptr || V <= 0 || N <= 0 ||
         opt.maxT <= 0 || opt.maxU <= 0 || (phase == kBackward && grads == nullptr))
@@ -341,8 +342,8 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
     struct Group {
         Workspace w;
         Dims d;
-        const T* acts;
-        T* grads;
+        const IO* acts;
+        IO* grads;
         const int *labels, *xlen, *ylen;
         T* costs;
         const T* scale_vec;
@@ -397,7 +398,7 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
     if (phase == kFull && grads && N >= 2 * kMaxGroups) {
         static const int forced = [] { const char* e = getenv("RNNT_B200_GROUPS"); return e ? atoi(e) : 0; }();
         const double lattice_us = 0.25 * (opt.maxT + opt.maxU) + 20.0;
-        const double stream_us = (double)rows64 * V * sizeof(T) * (grads ? 3.0 : 1.0) / 6.9e6;
+        const double stream_us = (double)rows64 * V * sizeof(IO) * (grads ? 3.0 : 1.0) / 6.9e6;
         if (stream_us > 400.0 && lattice_us > 0.08 * stream_us) groups = kMaxGroups;
         if (forced >= 1 && forced <= kMaxGroups) groups = forced;
         if (groups > 1 && !side_pool().ok) groups = 1;
@@ -409,7 +410,7 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
         const Group g = make_group(0, N);
         if (phase != kBackward) {
             // pass 1: log-softmax statistics + (blank, label) log-prob gather
-            stream_pass<T>(g.acts, nullptr, g.labels, g.xlen, g.ylen, g.w, scale, g.scale_vec, g.d, s, 1);
+            stream_pass<T, IO>(g.acts, nullptr, g.labels, g.xlen, g.ylen, g.w, scale, g.scale_vec, g.d, s, 1);
             mark(1, s);
             // lattice: alpha (and beta when gradients are or will be wanted)
             launch_lattice(g, s);
@@ -419,7 +420,7 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
         mark(2, s);
         // pass 2: dense gradient (+ zeros on padding)
         if (grads && phase != kForward) {
-            stream_pass<T>(g.acts, g.grads, g.labels, g.xlen, g.ylen, g.w, scale, g.scale_vec, g.d, s, 2);
+            stream_pass<T, IO>(g.acts, g.grads, g.labels, g.xlen, g.ylen, g.w, scale, g.scale_vec, g.d, s, 2);
             mark(3, s);
         }
     } else {
@@ -431,8 +432,8 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
         }
         // main stream: pass 1 of every group back to back; each group's lattice forks off behind it
         for (int k = 0; k < groups; ++k) {
-            stream_pass<T>(gs[k].acts, nullptr, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w, scale,
-                           gs[k].scale_vec, gs[k].d, s, 1);
+            stream_pass<T, IO>(gs[k].acts, nullptr, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w, scale,
+                               gs[k].scale_vec, gs[k].d, s, 1);
             cudaEventRecord(pool.forked[k], s);
             cudaStreamWaitEvent(pool.stream[k], pool.forked[k], 0);
             launch_lattice(gs[k], pool.stream[k]);
@@ -444,8 +445,8 @@ rnntStatus_t run(const T* acts, T* grads, const int* labels, const int* ylen, co
             cudaStreamWaitEvent(s, pool.joined[k], 0);
             if (k == 0) mark(2, s);
             if (grads && phase != kForward)
-                stream_pass<T>(gs[k].acts, gs[k].grads, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w,
-                               scale, gs[k].scale_vec, gs[k].d, s, 2);
+                stream_pass<T, IO>(gs[k].acts, gs[k].grads, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w,
+                                   scale, gs[k].scale_vec, gs[k].d, s, 2);
         }
         if (grads && phase != kForward) mark(3, s);
     }
@@ -552,6 +553,56 @@ rnntStatus_t rnnt_b200_backward_fp64(const double* const activations, double* gr
     return run<double>(activations, gradients, flat_labels, label_lengths, input_lengths,
                        alphabet_size, minibatch, nullptr, true, grad_scale, grad_costs_device,
                        kBackward, false, workspace, options);
+}
+
+// ---- 16-bit storage (bf16 / fp16 logits and gradients, fp32 arithmetic and costs) ---------------
+rnntStatus_t rnnt_b200_loss_async_16(int dtype, const void* activations, void* gradients,
+                                     const int* flat_labels, const int* label_lengths,
+                                     const int* input_lengths, int alphabet_size, int minibatch,
+                                     float* costs_device, float grad_scale, void* workspace,
+                                     rnntOptions options) {
+    if (dtype == RNNT_B200_BF16)
+        return run<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(activations),
+                                  static_cast<__nv_bfloat16*>(gradients), flat_labels, label_lengths,
+                                  input_lengths, alphabet_size, minibatch, costs_device, true, grad_scale,
+                                  nullptr, kFull, false, workspace, options);
+    if (dtype == RNNT_B200_FP16)
+        return run<__half>(static_cast<const __half*>(activations), static_cast<__half*>(gradients),
+                           flat_labels, label_lengths, input_lengths, alphabet_size, minibatch,
+                           costs_device, true, grad_scale, nullptr, kFull, false, workspace, options);
+    return RNNT_STATUS_INVALID_VALUE;
+}
+
+rnntStatus_t rnnt_b200_forward_16(int dtype, const void* activations, const int* flat_labels,
+                                  const int* label_lengths, const int* input_lengths,
+                                  int alphabet_size, int minibatch, float* costs_device,
+                                  int prepare_backward, void* workspace, rnntOptions options) {
+    if (dtype == RNNT_B200_BF16)
+        return run<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(activations), nullptr, flat_labels,
+                                  label_lengths, input_lengths, alphabet_size, minibatch, costs_device,
+                                  true, 1.0f, nullptr, kForward, prepare_backward != 0, workspace, options);
+    if (dtype == RNNT_B200_FP16)
+        return run<__half>(static_cast<const __half*>(activations), nullptr, flat_labels, label_lengths,
+                           input_lengths, alphabet_size, minibatch, costs_device, true, 1.0f, nullptr,
+                           kForward, prepare_backward != 0, workspace, options);
+    return RNNT_STATUS_INVALID_VALUE;
+}
+
+rnntStatus_t rnnt_b200_backward_16(int dtype, const void* activations, void* gradients,
+                                   const int* flat_labels, const int* label_lengths,
+                                   const int* input_lengths, int alphabet_size, int minibatch,
+                                   const float* grad_costs_device, float grad_scale, void* workspace,
+                                   rnntOptions options) {
+    if (dtype == RNNT_B200_BF16)
+        return run<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(activations),
+                                  static_cast<__nv_bfloat16*>(gradients), flat_labels, label_lengths,
+                                  input_lengths, alphabet_size, minibatch, nullptr, true, grad_scale,
+                                  grad_costs_device, kBackward, false, workspace, options);
+    if (dtype == RNNT_B200_FP16)
+        return run<__half>(static_cast<const __half*>(activations), static_cast<__half*>(gradients),
+                           flat_labels, label_lengths, input_lengths, alphabet_size, minibatch, nullptr,
+                           true, grad_scale, grad_costs_device, kBackward, false, workspace, options);
+    return RNNT_STATUS_INVALID_VALUE;
 }
 
 rnntStatus_t get_workspace_size(int maxT, int maxU, int minibatch, bool gpu, size_t* size_bytes,

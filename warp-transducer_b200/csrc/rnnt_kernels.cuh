@@ -57,9 +57,9 @@ constexpr int kRowThreads = 256;
 #ifndef RNNT_ROWSTATS_MINB
 #define RNNT_ROWSTATS_MINB 7
 #endif
-template <typename T, int VEC, int NV>
+template <typename T, int VEC, int NV, typename IO = T>
 __global__ void __launch_bounds__(kRowThreads, RNNT_ROWSTATS_MINB)
-rowstats_row_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
+rowstats_row_kernel(const IO* __restrict__ acts, const int* __restrict__ labels,
                     const int* __restrict__ xlen, const int* __restrict__ ylen,
                     typename Real<T>::pair* __restrict__ stat, typename Real<T>::pair* __restrict__ lp2,
                     const Dims d) {
@@ -73,7 +73,7 @@ rowstats_row_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
     utt_extent(d, xlen, ylen, b, Tb, Ub);
     if ((int)t >= Tb || (int)u >= Ub) return;  // padded cell: nothing to read (block-uniform)
     const int nv = d.V / VEC;
-    const T* row = acts + (uint64_t)r * d.V;
+    const IO* row = acts + (uint64_t)r * d.V;
     T m = R::neg_inf(), s = 0;
     for (int base = threadIdx.x; base < nv; base += kRowThreads * NV) {
         VecT<T, VEC> x[NV];
@@ -124,11 +124,11 @@ rowstats_row_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
             st.y = lse;
             stat[r] = st;
             typename R::pair lp;
-            lp.x = (__ldg(row + d.blank) - M) - lse;
+            lp.x = (ld_scalar<T>(row + d.blank) - M) - lse;
             lp.y = 0;
             if ((int)u < Ub - 1) {
                 const int y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
-                lp.y = (__ldg(row + y) - M) - lse;
+                lp.y = (ld_scalar<T>(row + y) - M) - lse;
             }
             lp2[skew(d, b, t, u)] = lp;
         }
@@ -144,9 +144,9 @@ rowstats_row_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
 // =================================================================================================
 constexpr int kVPL = 8;
 
-template <typename T, int VEC, int LPR>
+template <typename T, int VEC, int LPR, typename IO = T>
 __global__ void __launch_bounds__(256)
-rowstats_tile_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
+rowstats_tile_kernel(const IO* __restrict__ acts, const int* __restrict__ labels,
                      const int* __restrict__ xlen, const int* __restrict__ ylen,
                      typename Real<T>::pair* __restrict__ stat,
                      typename Real<T>::pair* __restrict__ lp2, const Dims d) {
@@ -169,7 +169,7 @@ rowstats_tile_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
             utt_extent(d, xlen, ylen, b, Tb, Ub);
             valid = (int)t < Tb && (int)u < Ub;
         }
-        const T* row = acts + (uint64_t)r * d.V;
+        const IO* row = acts + (uint64_t)r * d.V;
         VecT<T, VEC> x[kVPL];
 #pragma unroll
         for (int j = 0; j < kVPL; ++j) {
@@ -201,11 +201,11 @@ rowstats_tile_kernel(const T* __restrict__ acts, const int* __restrict__ labels,
             st.y = lse;
             stat[r] = st;
             typename R::pair lp;
-            lp.x = (__ldg(row + d.blank) - M) - lse;
+            lp.x = (ld_scalar<T>(row + d.blank) - M) - lse;
             lp.y = 0;
             if ((int)u < Ub - 1) {
                 const int y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
-                lp.y = (__ldg(row + y) - M) - lse;
+                lp.y = (ld_scalar<T>(row + y) - M) - lse;
             }
             lp2[skew(d, b, t, u)] = lp;
         }
@@ -461,9 +461,9 @@ __device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, 
 #ifndef RNNT_GRAD_MINB
 #define RNNT_GRAD_MINB 5
 #endif
-template <typename T, int VEC, int NV, bool SCALED>
+template <typename T, int VEC, int NV, bool SCALED, typename IO = T>
 __global__ void __launch_bounds__(kRowThreads, RNNT_GRAD_MINB)
-grad_row_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
+grad_row_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int* __restrict__ labels,
                 const int* __restrict__ xlen, const int* __restrict__ ylen,
                 const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
                 const double* __restrict__ betas, const double* __restrict__ llf, const T scale_in,
@@ -477,8 +477,8 @@ grad_row_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __
     utt_extent(d, xlen, ylen, b, Tb, Ub);
     const int nv = d.V / VEC;
     const int kb = d.blank;
-    const T* row = acts + (uint64_t)r * d.V;
-    T* grow = grads + (uint64_t)r * d.V;
+    const IO* row = acts + (uint64_t)r * d.V;
+    IO* grow = grads + (uint64_t)r * d.V;
     // per-utterance upstream gradient (autograd's grad_output) times the scalar factor
     const T scale = (SCALED && scale_vec) ? __ldg(scale_vec + b) * scale_in : scale_in;
     if ((int)t >= Tb || (int)u >= Ub) {
@@ -515,9 +515,9 @@ grad_row_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __
 }
 
 // Pass 2, short rows: same register tile as rowstats_tile_kernel.
-template <typename T, int VEC, int LPR, bool SCALED>
+template <typename T, int VEC, int LPR, bool SCALED, typename IO = T>
 __global__ void __launch_bounds__(256)
-grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
+grad_tile_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int* __restrict__ labels,
                  const int* __restrict__ xlen, const int* __restrict__ ylen,
                  const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
                  const double* __restrict__ betas, const double* __restrict__ llf, const T scale_in,
@@ -539,8 +539,8 @@ grad_tile_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* _
         d.divT.divmod(bt, b, t);
         int Tb, Ub;
         utt_extent(d, xlen, ylen, b, Tb, Ub);
-        const T* row = acts + (uint64_t)r * d.V;
-        T* grow = grads + (uint64_t)r * d.V;
+        const IO* row = acts + (uint64_t)r * d.V;
+        IO* grow = grads + (uint64_t)r * d.V;
         const T scale = (SCALED && scale_vec) ? __ldg(scale_vec + b) * scale_in : scale_in;
         if ((int)t >= Tb || (int)u >= Ub) {
             VecT<T, VEC> z;

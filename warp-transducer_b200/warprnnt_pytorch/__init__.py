@@ -40,7 +40,8 @@ class _RNNT(Function):
             raise ValueError("reduction must be 'none', 'sum' or 'mean'")
         minibatch_size = acts.size(0)
         need_grad = acts.requires_grad
-        costs = torch.empty(minibatch_size, dtype=acts.dtype, device=acts.device)
+        # bf16 / fp16 logits: arithmetic, lattice and costs are fp32 (6 B per logit instead of 12)
+        costs = torch.empty(minibatch_size, dtype=warp_rnnt.costs_dtype(acts), device=acts.device)
         ws = warp_rnnt.gpu_rnnt_forward(acts, labels, act_lens, label_lens, costs, blank,
                                         prepare_backward=need_grad)
         if need_grad:
@@ -60,7 +61,7 @@ class _RNNT(Function):
         # reference :47-50: grads.mul_(grad_output.view(-1,1,1,1)); here the factor rides in the kernel
         acts, labels, act_lens, label_lens = ctx.saved_tensors
         n = acts.size(0)
-        g = grad_output.reshape(-1).to(device=acts.device, dtype=acts.dtype)
+        g = grad_output.reshape(-1).to(device=acts.device, dtype=warp_rnnt.costs_dtype(acts))
         g = g.expand(n).contiguous() if g.numel() == 1 else g.contiguous()
         grads = torch.empty_like(acts)   # the kernel defines every element (zeros on padding)
         warp_rnnt.gpu_rnnt_backward(acts, labels, act_lens, label_lens, grads, g, ctx.blank,

@@ -50,6 +50,13 @@ for _name, _ct in (("rnnt_b200_backward", C.c_float), ("rnnt_b200_backward_fp64"
     _f = getattr(_lib, _name)
     _f.restype = C.c_int
     _f.argtypes = [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _ct, _P, rnntOptions]
+_lib.rnnt_b200_loss_async_16.restype = C.c_int
+_lib.rnnt_b200_loss_async_16.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P, rnntOptions]
+_lib.rnnt_b200_forward_16.restype = C.c_int
+_lib.rnnt_b200_forward_16.argtypes = [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, rnntOptions]
+_lib.rnnt_b200_backward_16.restype = C.c_int
+_lib.rnnt_b200_backward_16.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P, rnntOptions]
+RNNT_B200_BF16, RNNT_B200_FP16 = 1, 2
 _lib.get_workspace_size.restype = C.c_int
 _lib.get_workspace_size.argtypes = [C.c_int, C.c_int, C.c_int, C.c_bool, C.POINTER(C.c_size_t), C.c_size_t]
 _lib.get_warprnnt_version.restype = C.c_int
@@ -150,7 +157,10 @@ def gpu_rnnt_async(acts, labels, input_lengths, label_lengths, costs, grads, bla
     """Extension: no host synchronisation, `costs` on the device, gradients pre-multiplied by
     `grad_scale`.  Returns the workspace tensor (keep it alive until the stream has run)."""
     N, T, U, V = acts.shape
-    if acts.dtype == torch.float32:
+    code = _code16(acts)
+    if code:
+        esz = 4
+    elif acts.dtype == torch.float32:
         fn, esz = _lib.compute_rnnt_loss_async, 4
     elif acts.dtype == torch.float64:
         fn, esz = _lib.compute_rnnt_loss_async_fp64, 8
@@ -160,12 +170,22 @@ def gpu_rnnt_async(acts, labels, input_lengths, label_lengths, costs, grads, bla
         need = workspace_size(T, U, N, esz)
         if workspace is None or workspace.numel() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=acts.device)
-        st = fn(acts.data_ptr(), _ptr(grads), _labels_ptr(labels), label_lengths.data_ptr(),
+        args = (acts.data_ptr(), _ptr(grads), _labels_ptr(labels), label_lengths.data_ptr(),
                 input_lengths.data_ptr(), V, N, costs.data_ptr(), grad_scale, workspace.data_ptr(),
                 _options(acts, blank_label))
+        st = _lib.rnnt_b200_loss_async_16(code, *args) if code else fn(*args)
     if st != RNNT_STATUS_SUCCESS:
         raise RuntimeError("compute_rnnt_loss_async failed: " + status_string(st))
     return workspace
+
+
+def _code16(acts):
+    return {torch.bfloat16: RNNT_B200_BF16, torch.float16: RNNT_B200_FP16}.get(acts.dtype)
+
+
+def costs_dtype(acts):
+    """dtype of the per-utterance costs for a given activation dtype (fp32 for 16-bit storage)."""
+    return torch.float32 if _code16(acts) else acts.dtype
 
 
 def _pick(acts, f32, f64):
@@ -181,14 +201,16 @@ def gpu_rnnt_forward(acts, labels, input_lengths, label_lengths, costs, blank_la
     """Training-step split, first half: statistics + lattices into `workspace`, costs on the
     device, no synchronisation.  Returns the workspace tensor (hand it to gpu_rnnt_backward)."""
     N, T, U, V = acts.shape
-    fn, esz = _pick(acts, "rnnt_b200_forward", "rnnt_b200_forward_fp64")
+    code = _code16(acts)
+    fn, esz = (None, 4) if code else _pick(acts, "rnnt_b200_forward", "rnnt_b200_forward_fp64")
     with torch.cuda.device(acts.device):
         need = workspace_size(T, U, N, esz)
         if workspace is None or workspace.numel() < need:
             workspace = torch.empty(need, dtype=torch.uint8, device=acts.device)
-        st = fn(acts.data_ptr(), _labels_ptr(labels), label_lengths.data_ptr(), input_lengths.data_ptr(),
+        args = (acts.data_ptr(), _labels_ptr(labels), label_lengths.data_ptr(), input_lengths.data_ptr(),
                 V, N, costs.data_ptr(), 1 if prepare_backward else 0, workspace.data_ptr(),
                 _options(acts, blank_label))
+        st = _lib.rnnt_b200_forward_16(code, *args) if code else fn(*args)
     if st != RNNT_STATUS_SUCCESS:
         raise RuntimeError("rnnt_b200_forward failed: " + status_string(st))
     return workspace
@@ -199,11 +221,13 @@ def gpu_rnnt_backward(acts, labels, input_lengths, label_lengths, grads, grad_co
     """Second half: grads[b] = grad_scale * grad_costs[b] * d cost[b] / d acts[b] from the lattices
     gpu_rnnt_forward left in `workspace` (grad_costs: device tensor [N] or None for ones)."""
     N, T, U, V = acts.shape
-    fn, esz = _pick(acts, "rnnt_b200_backward", "rnnt_b200_backward_fp64")
+    code = _code16(acts)
+    fn = None if code else _pick(acts, "rnnt_b200_backward", "rnnt_b200_backward_fp64")[0]
     with torch.cuda.device(acts.device):
-        st = fn(acts.data_ptr(), grads.data_ptr(), _labels_ptr(labels), label_lengths.data_ptr(),
+        args = (acts.data_ptr(), grads.data_ptr(), _labels_ptr(labels), label_lengths.data_ptr(),
                 input_lengths.data_ptr(), V, N, _ptr(grad_costs), grad_scale, workspace.data_ptr(),
                 _options(acts, blank_label))
+        st = _lib.rnnt_b200_backward_16(code, *args) if code else fn(*args)
     if st != RNNT_STATUS_SUCCESS:
         raise RuntimeError("rnnt_b200_backward failed: " + status_string(st))
     return 0
