@@ -157,7 +157,7 @@ bool is_device_pointer(const void* p) {
 template <typename T, int VEC, int NV, typename IO>
 void launch_rowstats_row(const IO* acts, const int* labels, const int* xlen, const int* ylen,
                          const Workspace& w, const Dims& d, cudaStream_t s) {
-    rowstats_row_kernel<T, VEC, NV, IO><<<d.rows, kRowThreads, 0, s>>>(
+    rowstats_row_kernel<T, VEC, NV, IO><<<d.rows, RowThreads<IO>::value, 0, s>>>(
         acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
         static_cast<typename Real<T>::pair*>(w.lp2), d);
     ++g_last_launches;
@@ -168,7 +168,7 @@ void launch_grad_row(const IO* acts, IO* grads, const int* labels, const int* xl
                      const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s) {
     auto k = (scale != T(1) || scale_vec) ? grad_row_kernel<T, VEC, NV, true, IO>
                                           : grad_row_kernel<T, VEC, NV, false, IO>;
-    k<<<d.rows, kRowThreads, 0, s>>>(acts, grads, labels, xlen, ylen,
+    k<<<d.rows, RowThreads<IO>::value, 0, s>>>(acts, grads, labels, xlen, ylen,
                                       static_cast<const typename Real<T>::pair*>(w.stat), w.alphas,
                                       w.betas, w.llf, scale, scale_vec, d);
     ++g_last_launches;
@@ -214,13 +214,13 @@ void stream_passes(const IO* acts, IO* grads, const int* labels, const int* xlen
                    const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s, int pass) {
     const int nv = d.V / VEC;
     if (nv > 32 * kVPL) {  // long rows: CTA per row; NV = vectors per thread per trip
-        const int per_thread = (nv + kRowThreads - 1) / kRowThreads;
+        const int per_thread = (nv + RowThreads<IO>::value - 1) / RowThreads<IO>::value;
 #define B200_ROW(NVV)                                                                             \
     do {                                                                                          \
         if (pass == 1) launch_rowstats_row<T, VEC, NVV, IO>(acts, labels, xlen, ylen, w, d, s);       \
         else launch_grad_row<T, VEC, NVV, IO>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s);       \
     } while (0)
-        if (sizeof(IO) == 4 && VEC == 4) {  // the fp32 fast path gets an exact register count
+        if (sizeof(IO) <= 4 && VEC == 16 / (int)sizeof(IO)) {  // 16-B fast paths get an exact register count
             switch (per_thread) {
                 case 1: B200_ROW(1); break;
                 case 2: B200_ROW(2); break;

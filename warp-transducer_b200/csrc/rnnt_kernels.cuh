@@ -52,18 +52,21 @@ __device__ __forceinline__ void utt_extent(const Dims& d, const int* __restrict_
 // max / sum exp(x-max) from registers; trips are merged online.  Block combine: warp shuffles, one
 // shared-memory exchange, one __syncthreads.
 // =================================================================================================
-constexpr int kRowThreads = 256;
+// threads per CTA-per-row block: 256 for 4/8-byte logits, 128 for 16-bit logits (a 16-bit row is
+// half as long, so the smaller block keeps ~5 16-B loads in flight per thread)
+template <typename IO> struct RowThreads { static constexpr int value = sizeof(IO) >= 4 ? 256 : 128; };
 
 #ifndef RNNT_ROWSTATS_MINB
 #define RNNT_ROWSTATS_MINB 7
 #endif
 template <typename T, int VEC, int NV, typename IO = T>
-__global__ void __launch_bounds__(kRowThreads, RNNT_ROWSTATS_MINB)
+__global__ void __launch_bounds__(RowThreads<IO>::value, (sizeof(IO) >= 4 ? RNNT_ROWSTATS_MINB : 8))
 rowstats_row_kernel(const IO* __restrict__ acts, const int* __restrict__ labels,
                     const int* __restrict__ xlen, const int* __restrict__ ylen,
                     typename Real<T>::pair* __restrict__ stat, typename Real<T>::pair* __restrict__ lp2,
                     const Dims d) {
     using R = Real<T>;
+    constexpr int kRowThreads = RowThreads<IO>::value;
     __shared__ T sh_m[kRowThreads / 32], sh_s[kRowThreads / 32];
     const uint32_t r = blockIdx.x;
     uint32_t bt, u, b, t;
@@ -462,13 +465,14 @@ __device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, 
 #define RNNT_GRAD_MINB 5
 #endif
 template <typename T, int VEC, int NV, bool SCALED, typename IO = T>
-__global__ void __launch_bounds__(kRowThreads, RNNT_GRAD_MINB)
+__global__ void __launch_bounds__(RowThreads<IO>::value, (sizeof(IO) >= 4 ? RNNT_GRAD_MINB : 6))
 grad_row_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int* __restrict__ labels,
                 const int* __restrict__ xlen, const int* __restrict__ ylen,
                 const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
                 const double* __restrict__ betas, const double* __restrict__ llf, const T scale_in,
                 const T* __restrict__ scale_vec,
                 const Dims d) {
+    constexpr int kRowThreads = RowThreads<IO>::value;
     const uint32_t r = d.rows - 1 - blockIdx.x;
     uint32_t bt, u, b, t;
     d.divU.divmod(r, bt, u);
