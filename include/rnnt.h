@@ -202,6 +202,23 @@ rnntStatus_t rnnt_b200_backward_16(int dtype, const void* activations, void* gra
                                    const float* grad_costs_device, float grad_scale, void* workspace,
                                    struct rnntOptions options);
 
+/*
+ * Additive joint network, logits never materialised: for models whose logits
+ * are  h[b,t,u,k] = trans[b,t,k] + pred[b,u,k]  (how the reference's own timing script builds them,
+ * pytorch_binding/test/test_time.py:73).  trans [minibatch,maxT,V], pred [minibatch,maxU,V];
+ * outputs costs_device [minibatch] and, when both gradient pointers are non-NULL,
+ * grad_trans = grad_scale * d cost/d trans, grad_pred likewise (docs/rnnt_notes.tex:147-153).
+ * All pointers DEVICE, fp32, no synchronisation.  Workspace from rnnt_b200_add_joint_workspace_size.
+ * HBM traffic is O(N (T+U) V) instead of O(N T U V).
+ */
+rnntStatus_t rnnt_b200_add_joint_loss(const float* trans, const float* pred, float* grad_trans,
+                                      float* grad_pred, const int* flat_labels,
+                                      const int* label_lengths, const int* input_lengths,
+                                      int alphabet_size, int minibatch, float* costs_device,
+                                      float grad_scale, void* workspace, struct rnntOptions options);
+rnntStatus_t rnnt_b200_add_joint_workspace_size(int maxT, int maxU, int minibatch, int alphabet_size,
+                                                size_t* size_bytes);
+
 /* Number of kernels the last compute call on this thread launched (bench.py's gpu_launches). */
 int rnnt_b200_last_launch_count(void);
 

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/rnnt.h"
+#include "rnnt_joint.cuh"
 #include "rnnt_kernels.cuh"
 
 using namespace b200rnnt;
@@ -462,6 +463,113 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
     return RNNT_STATUS_SUCCESS;
 }
 
+// ---- additive-joint variant (rnnt_joint.cuh) ----------------------------------------------------
+struct JointWorkspace {
+    float *ef, *eg, *mf, *mg, *inv_s, *wm, *bk, *lb;
+    float2* lp2;
+    double *alphas, *betas, *llf, *llb;
+    size_t bytes;
+};
+JointWorkspace carve_joint(void* base, int N, int T, int U, int V) {
+    JointWorkspace w;
+    size_t off = align_up(reinterpret_cast<uintptr_t>(base), 256) - reinterpret_cast<uintptr_t>(base);
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t n) {
+        void* q = p ? p + off : nullptr;
+        off = align_up(off + n, 256);
+        return q;
+    };
+    const size_t C = (size_t)N * T * U, D = (size_t)N * (T + U - 1) * U;
+    w.ef = static_cast<float*>(take((size_t)N * T * V * 4));
+    w.eg = static_cast<float*>(take((size_t)N * U * V * 4));
+    w.mf = static_cast<float*>(take((size_t)N * T * 4));
+    w.mg = static_cast<float*>(take((size_t)N * U * 4));
+    w.inv_s = static_cast<float*>(take(C * 4));
+    w.wm = static_cast<float*>(take(C * 4));
+    w.bk = static_cast<float*>(take(C * 4));
+    w.lb = static_cast<float*>(take(C * 4));
+    w.lp2 = static_cast<float2*>(take(D * 8));
+    w.alphas = static_cast<double*>(take(D * 8));
+    w.betas = static_cast<double*>(take(D * 8));
+    w.llf = static_cast<double*>(take((size_t)N * 8));
+    w.llb = static_cast<double*>(take((size_t)N * 8));
+    w.bytes = off + 256;
+    return w;
+}
+
+rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG, const int* labels,
+                           const int* ylen, const int* xlen, int V, int N, float* costs, float scale,
+                           void* workspace, rnntOptions opt) {
+    if (!f || !g || !labels || !ylen || !xlen || !costs || !workspace || V <= 0 || N <= 0 ||
+        opt.maxT <= 0 || opt.maxU <= 0 || (dF == nullptr) != (dG == nullptr))
+        return RNNT_STATUS_INVALID_VALUE;
+    if (opt.loc != RNNT_GPU) return opt.loc == RNNT_CPU ? RNNT_STATUS_EXECUTION_FAILED : RNNT_STATUS_INVALID_VALUE;
+    const int T = opt.maxT, U = opt.maxU;
+    const uint64_t rows64 = (uint64_t)N * T * U;
+    if (rows64 >= (1ull << 31) || U > 1024 || opt.blank_label < 0 || opt.blank_label >= V)
+        return RNNT_STATUS_INVALID_VALUE;
+    g_last_launches = 0;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(opt.stream);
+    JointWorkspace w = carve_joint(workspace, N, T, U, V);
+    JointDims jd{N, T, U, V, opt.blank_label};
+    Dims d;
+    d.N = N;
+    d.maxT = T;
+    d.maxU = U;
+    d.V = V;
+    d.blank = opt.blank_label;
+    d.rows = (uint32_t)rows64;
+    d.divU = FastDiv(U);
+    d.divT = FastDiv(T);
+    const bool want_grad = dF != nullptr;
+
+    // J1: factor-wise max and exponentials
+    joint_prep_kernel<<<(N * T + 7) / 8, 256, 0, s>>>(f, w.ef, w.mf, N * T, V);
+    joint_prep_kernel<<<(N * U + 7) / 8, 256, 0, s>>>(g, w.eg, w.mg, N * U, V);
+    // J2: S = Ef . Eg^T  -> lse, lattice log-prob pairs
+    {
+        Operand A{w.ef, (size_t)T * V, V, 1}, B{w.eg, (size_t)U * V, V, 1};
+        EpiStats epi{f, g, w.mf, w.mg, labels, xlen, ylen, w.inv_s, w.lp2, jd, d};
+        dim3 grid((U + 63) / 64, (T + 63) / 64, N);
+        joint_gemm_kernel<<<grid, 256, 0, s>>>(A, B, T, U, V, epi);
+    }
+    // lattice (same kernel as the dense path)
+    {
+        const int threads = (U + 31) / 32 * 32;
+        dim3 grid(N, want_grad ? 2 : 1);
+        const size_t ring = (size_t)kRing * threads * sizeof(float2);
+        auto launch = [&](auto kernel) {
+            static thread_local size_t opted = 0;
+            if (ring > 48 * 1024 && ring > opted) {
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+                opted = ring;
+            }
+            kernel<<<grid, threads, ring, s>>>(w.lp2, xlen, ylen, w.alphas, w.betas, w.llf, w.llb, costs, d);
+        };
+        if (threads > 32) launch(lattice_kernel<float, true>);
+        else launch(lattice_kernel<float, false>);
+    }
+    g_last_launches += 4;
+    if (want_grad) {
+        joint_weights_kernel<<<(d.rows + 255) / 256, 256, 0, s>>>(w.lp2, w.alphas, w.betas, w.llf, w.inv_s,
+                                                                 xlen, ylen, w.wm, w.bk, w.lb, scale, d);
+        {   // dF = Ef (.) (Wm . Eg)
+            Operand A{w.wm, (size_t)T * U, U, 1}, B{w.eg, (size_t)U * V, 1, V};
+            dim3 grid((V + 63) / 64, (T + 63) / 64, N);
+            joint_gemm_kernel<<<grid, 256, 0, s>>>(A, B, T, V, U, EpiGrad{w.ef, dF, T, V});
+        }
+        {   // dG = Eg (.) (Wm^T . Ef)
+            Operand A{w.wm, (size_t)T * U, 1, U}, B{w.ef, (size_t)T * V, 1, V};
+            dim3 grid((V + 63) / 64, (U + 63) / 64, N);
+            joint_gemm_kernel<<<grid, 256, 0, s>>>(A, B, U, V, T, EpiGrad{w.eg, dG, U, V});
+        }
+        joint_sparse_f_kernel<<<(N * T + 127) / 128, 128, 0, s>>>(dF, w.bk, w.lb, labels, ylen, jd);
+        joint_sparse_g_kernel<<<(N * U + 127) / 128, 128, 0, s>>>(dG, w.bk, w.lb, labels, xlen, ylen, jd);
+        g_last_launches += 5;
+    }
+    return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
+}
+
 }  // namespace
 
 extern "C" {
@@ -603,6 +711,24 @@ rnntStatus_t rnnt_b200_backward_16(int dtype, const void* activations, void* gra
                            flat_labels, label_lengths, input_lengths, alphabet_size, minibatch, nullptr,
                            true, grad_scale, grad_costs_device, kBackward, false, workspace, options);
     return RNNT_STATUS_INVALID_VALUE;
+}
+
+// ---- additive joint network, logits never materialised -------------------------------------------
+rnntStatus_t rnnt_b200_add_joint_loss(const float* trans, const float* pred, float* grad_trans,
+                                      float* grad_pred, const int* flat_labels,
+                                      const int* label_lengths, const int* input_lengths,
+                                      int alphabet_size, int minibatch, float* costs_device,
+                                      float grad_scale, void* workspace, rnntOptions options) {
+    return run_add_joint(trans, pred, grad_trans, grad_pred, flat_labels, label_lengths, input_lengths,
+                         alphabet_size, minibatch, costs_device, grad_scale, workspace, options);
+}
+
+rnntStatus_t rnnt_b200_add_joint_workspace_size(int maxT, int maxU, int minibatch, int alphabet_size,
+                                                size_t* size_bytes) {
+    if (minibatch <= 0 || maxT <= 0 || maxU <= 0 || alphabet_size <= 0 || size_bytes == nullptr)
+        return RNNT_STATUS_INVALID_VALUE;
+    *size_bytes = carve_joint(nullptr, minibatch, maxT, maxU, alphabet_size).bytes;
+    return RNNT_STATUS_SUCCESS;
 }
 
 rnntStatus_t get_workspace_size(int maxT, int maxU, int minibatch, bool gpu, size_t* size_bytes,

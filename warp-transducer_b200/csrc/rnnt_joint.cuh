@@ -1,0 +1,214 @@
+// rnnt_joint.cuh — RNN-T loss for the ADDITIVE joint network, logits never materialised
+// (the reference's own timing script builds its logits this way,
+// pytorch_binding/test/test_time.py:73: acts = trans.unsqueeze(2) + pred.unsqueeze(1); the
+// gradients w.r.t. the two factors are docs/rnnt_notes.tex:147-153).
+//
+//   h[b,t,u,k] = f[b,t,k] + g[b,u,k]
+//
+// Because exp(f+g) = exp(f)·exp(g), every V-length reduction of the standard path factorises:
+//   S(t,u)   = sum_k e^{f_tk - mf_t} e^{g_uk - mg_u}            = (Ef · Eg^T)[t,u]
+//   lse(t,u) = mf_t + mg_u + log S(t,u)
+//   dL/df_tk = Ef_tk · sum_u Wm(t,u) Eg_uk  - (blank / label terms),   Wm = e^{alpha+beta-ll} / S
+//   dL/dg_uk = Eg_uk · sum_t Wm(t,u) Ef_tk  - (blank / label terms)
+// i.e. three small batched fp32 GEMMs around the SAME lattice kernel, and HBM traffic of
+// O(N (T+U) V) instead of O(N T U V): 0.44 GB instead of 24 GB on the README large-vocabulary shape.
+// fp32 FMA GEMMs, not tensor cores: the sums feed a logarithm and need ~1e-6 relative accuracy,
+// and the whole contraction is only 3 x 2 GFMA.
+// Limitation (documented in DESIGN.md): the factor-wise maxima bound the terms by 1 but not from
+// below; if max_k(f+g) is more than ~85 nats under mf+mg the fp32 sum underflows.
+#pragma once
+#include "rnnt_kernels.cuh"
+
+namespace b200rnnt {
+
+struct JointDims {
+    int N, T, U, V, blank;
+};
+
+// ---- J1: per row of a factor: max and exp(x - max) ------------------------------------------------
+// one warp per row of V elements (rows = N*T for f, N*U for g)
+__global__ void __launch_bounds__(256)
+joint_prep_kernel(const float* __restrict__ x, float* __restrict__ e, float* __restrict__ mx, int rows, int V) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* p = x + (size_t)row * V;
+    float m = -INFINITY;
+    for (int k = lane; k < V; k += 32) m = fmaxf(m, __ldg(p + k));
+    m = group_max<32>(m);
+    const float mz = (m == -INFINITY) ? 0.0f : m;
+    float* q = e + (size_t)row * V;
+    for (int k = lane; k < V; k += 32) q[k] = Real<float>::exp(__ldg(p + k) - mz);
+    if (lane == 0) mx[row] = m;
+}
+
+// ---- generic batched fp32 GEMM  C[b](m,n) = sum_k A[b](m,k) * B[b](k,n), strided operands ----------
+// 64x64 tile, 16-deep k-chunks through shared memory, 256 threads x (4x4) outputs.  Epilogue
+// functor Epi(b, m, n, acc) writes the result.
+struct Operand {
+    const float* p;
+    size_t batch;  // elements between batches
+    int s_outer;   // stride of the m (A) / n (B) index
+    int s_k;       // stride of the k index
+};
+
+template <typename Epi>
+__global__ void __launch_bounds__(256)
+joint_gemm_kernel(Operand A, Operand B, int M, int Nn, int K, Epi epi) {
+    __shared__ float sa[16][64 + 1], sb[16][64 + 1];
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const float* a = A.p + (size_t)b * A.batch;
+    const float* bb = B.p + (size_t)b * B.batch;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4x4 outputs each
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        // cooperative loads: 64x16 of A and of B, 4 elements per thread each
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            // two index orders so that whichever stride is 1 gives coalesced reads
+            int r, kk;
+            if (A.s_k == 1) { kk = i & 15; r = i >> 4; } else { r = i & 63; kk = i >> 6; }
+            const int m = m0 + r, k = k0 + kk;
+            sa[kk][r] = (m < M && k < K) ? __ldg(a + (size_t)m * A.s_outer + (size_t)k * A.s_k) : 0.0f;
+            if (B.s_k == 1) { kk = i & 15; r = i >> 4; } else { r = i & 63; kk = i >> 6; }
+            const int n = n0 + r, k2 = k0 + kk;
+            sb[kk][r] = (n < Nn && k2 < K) ? __ldg(bb + (size_t)n * B.s_outer + (size_t)k2 * B.s_k) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = sa[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = sb[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < M && n < Nn) epi(b, m, n, acc[i][j]);
+        }
+}
+
+// ---- J2 epilogue: S -> lse, lattice log-prob pair (diagonal-major), keep 1/S -----------------------
+struct EpiStats {
+    const float *f, *g, *mf, *mg;
+    const int *labels, *xlen, *ylen;
+    float* inv_s;  // [N,T,U]
+    float2* lp2;   // diagonal-major lattice pairs
+    JointDims jd;
+    Dims d;        // lattice geometry (maxT = T, maxU = U)
+    __device__ void operator()(int b, int t, int u, float S) const {
+        int Tb, Ub;
+        utt_extent(d, xlen, ylen, b, Tb, Ub);
+        const size_t cell = ((size_t)b * jd.T + t) * jd.U + u;
+        if (t >= Tb || u >= Ub) {
+            inv_s[cell] = 0.0f;
+            return;
+        }
+        const float mft = mf[(size_t)b * jd.T + t], mgu = mg[(size_t)b * jd.U + u];
+        const float lse = mft + mgu + logf(S);
+        inv_s[cell] = 1.0f / S;
+        const float* fr = f + ((size_t)b * jd.T + t) * jd.V;
+        const float* gr = g + ((size_t)b * jd.U + u) * jd.V;
+        float2 lp;
+        lp.x = (__ldg(fr + jd.blank) + __ldg(gr + jd.blank)) - lse;
+        lp.y = 0.0f;
+        if (u < Ub - 1) {
+            const int y = __ldg(labels + (size_t)b * (jd.U > 1 ? jd.U - 1 : 0) + u);
+            lp.y = (__ldg(fr + y) + __ldg(gr + y)) - lse;
+        }
+        lp2[skew(d, b, t, u)] = lp;
+    }
+};
+
+// ---- J3: per cell weights from the lattices ---------------------------------------------------------
+//   Wm = e^{alpha+beta-ll} / S ;  Bk = blank-transition occupancy ;  Lb = label-transition occupancy
+__global__ void __launch_bounds__(256)
+joint_weights_kernel(const float2* __restrict__ lp2, const double* __restrict__ alphas,
+                     const double* __restrict__ betas, const double* __restrict__ llf,
+                     const float* __restrict__ inv_s, const int* __restrict__ xlen,
+                     const int* __restrict__ ylen, float* __restrict__ Wm, float* __restrict__ Bk,
+                     float* __restrict__ Lb, const float scale, const Dims d) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.rows) return;
+    uint32_t bt, u, b, t;
+    d.divU.divmod(r, bt, u);
+    d.divT.divmod(bt, b, t);
+    int Tb, Ub;
+    utt_extent(d, xlen, ylen, b, Tb, Ub);
+    float w = 0.0f, bk = 0.0f, lb = 0.0f;
+    if ((int)t < Tb && (int)u < Ub) {
+        const size_t q = skew(d, b, t, u);
+        const float2 lp = lp2[q];
+        const double occ = alphas[q] - llf[b];
+        w = scale * expf((float)(occ + betas[q])) * inv_s[r];
+        if ((int)t < Tb - 1) bk = scale * expf((float)(occ + betas[q + d.maxU]) + lp.x);
+        else if ((int)u == Ub - 1) bk = scale * expf((float)occ + lp.x);
+        if ((int)u < Ub - 1) lb = scale * expf((float)(occ + betas[q + d.maxU + 1]) + lp.y);
+    }
+    Wm[r] = w;
+    Bk[r] = bk;
+    Lb[r] = lb;
+}
+
+// ---- J4/J5 epilogue: multiply by the factor's own exponentials -------------------------------------
+struct EpiGrad {
+    const float* e;  // Ef [N,T,V] (or Eg [N,U,V])
+    float* out;      // dF (or dG), same shape
+    int rows, V;     // rows per batch (T or U)
+    __device__ void operator()(int b, int m, int n, float acc) const {
+        const size_t i = ((size_t)b * rows + m) * V + n;
+        out[i] = e[i] * acc;
+    }
+};
+
+// ---- J6: the blank / label terms (sparse in k) -------------------------------------------------------
+// one thread per (b,t) for dF and per (b,u) for dG; sequential over the short other axis so repeated
+// labels accumulate without atomics.
+__global__ void __launch_bounds__(128)
+joint_sparse_f_kernel(float* __restrict__ dF, const float* __restrict__ Bk, const float* __restrict__ Lb,
+                      const int* __restrict__ labels, const int* __restrict__ ylen, const JointDims jd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= jd.N * jd.T) return;
+    const int b = i / jd.T;
+    const int Ub = min(max(__ldg(ylen + b) + 1, 1), jd.U);
+    float* row = dF + (size_t)i * jd.V;
+    const float* bk = Bk + (size_t)i * jd.U;
+    const float* lb = Lb + (size_t)i * jd.U;
+    float sb = 0.0f;
+    for (int u = 0; u < Ub; ++u) sb += bk[u];
+    row[jd.blank] -= sb;
+    for (int u = 0; u < Ub - 1; ++u) row[__ldg(labels + (size_t)b * (jd.U - 1) + u)] -= lb[u];
+}
+
+__global__ void __launch_bounds__(128)
+joint_sparse_g_kernel(float* __restrict__ dG, const float* __restrict__ Bk, const float* __restrict__ Lb,
+                      const int* __restrict__ labels, const int* __restrict__ xlen,
+                      const int* __restrict__ ylen, const JointDims jd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= jd.N * jd.U) return;
+    const int b = i / jd.U, u = i % jd.U;
+    const int Tb = min(max(__ldg(xlen + b), 1), jd.T);
+    const int Ub = min(max(__ldg(ylen + b) + 1, 1), jd.U);
+    if (u >= Ub) return;
+    float* row = dG + (size_t)i * jd.V;
+    float sb = 0.0f, sl = 0.0f;
+    for (int t = 0; t < Tb; ++t) {
+        const size_t c = ((size_t)b * jd.T + t) * jd.U + u;
+        sb += Bk[c];
+        sl += Lb[c];
+    }
+    row[jd.blank] -= sb;
+    if (u < Ub - 1) row[__ldg(labels + (size_t)b * (jd.U - 1) + u)] -= sl;
+}
+
+}  // namespace b200rnnt

@@ -1,0 +1,115 @@
+"""RNN-T loss for an ADDITIVE joint network without materialising the [N,T,U,V] logits
+(SURVEY.md §8(f).2).  The reference's own timing script forms its logits as
+``acts = trans.unsqueeze(2) + pred.unsqueeze(1)`` (pytorch_binding/test/test_time.py:73) and then
+calls RNNTLoss on the 4-D tensor; this operator takes the two factors directly:
+
+    loss = AddJointRNNTLoss(blank=0, reduction='mean')(trans, pred, labels, act_lens, label_lens)
+
+trans [N,T,V], pred [N,U,V] fp32 CUDA, same label/length conventions and input checks as RNNTLoss.
+Equivalent to RNNTLoss()(trans.unsqueeze(2) + pred.unsqueeze(1), ...) with gradients reduced to
+the factors, at O(N (T+U) V) memory traffic.
+"""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+from torch.nn import Module
+
+from . import check_contiguous, check_dim, check_type, warp_rnnt
+
+_lib = warp_rnnt.lib()
+_P = C.c_void_p
+_lib.rnnt_b200_add_joint_loss.restype = C.c_int
+_lib.rnnt_b200_add_joint_loss.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P,
+                                          warp_rnnt.rnntOptions]
+_lib.rnnt_b200_add_joint_workspace_size.restype = C.c_int
+_lib.rnnt_b200_add_joint_workspace_size.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+
+
+def certify_joint_inputs(trans, pred, labels, lengths, label_lengths):
+    check_type(labels, torch.int32, "labels")
+    check_type(label_lengths, torch.int32, "label_lengths")
+    check_type(lengths, torch.int32, "lengths")
+    for t, n in ((trans, "trans"), (pred, "pred"), (labels, "labels"), (lengths, "lengths"),
+                 (label_lengths, "label_lengths")):
+        check_contiguous(t, n)
+    check_dim(trans, 3, "trans")
+    check_dim(pred, 3, "pred")
+    check_dim(labels, 2, "labels")
+    if trans.dtype != torch.float32 or pred.dtype != torch.float32:
+        raise TypeError("trans and pred must be float32")
+    if not (trans.shape[0] == pred.shape[0] == lengths.shape[0] == label_lengths.shape[0]):
+        raise ValueError("must have a length and a label length per example.")
+    if trans.shape[2] != pred.shape[2]:
+        raise ValueError("trans and pred must share the vocabulary dimension")
+    max_T, max_U = torch.stack((lengths.max(), label_lengths.max())).tolist()
+    if trans.shape[1] != max_T:
+        raise ValueError("Input length mismatch")
+    if pred.shape[1] != max_U + 1:
+        raise ValueError("Output length mismatch")
+
+
+def add_joint_call(trans, pred, labels, act_lens, label_lens, costs, dtrans, dpred, blank, scale):
+    """Raw call of rnnt_b200_add_joint_loss on CUDA tensors (no checks, no synchronisation)."""
+    N, T, V = trans.shape
+    U = pred.shape[1]
+    n = C.c_size_t(0)
+    st = _lib.rnnt_b200_add_joint_workspace_size(T, U, N, V, C.byref(n))
+    if st != 0:
+        raise ValueError("workspace size: " + warp_rnnt.status_string(st))
+    with torch.cuda.device(trans.device):
+        ws = torch.empty(n.value, dtype=torch.uint8, device=trans.device)
+        opt = warp_rnnt.rnntOptions(loc=1, num_threads=0,
+                                    stream=torch.cuda.current_stream(trans.device).cuda_stream,
+                                    blank_label=blank, maxT=T, maxU=U, batch_first=True)
+        lab = labels.data_ptr() if labels.numel() else labels.new_zeros(1).data_ptr()
+        st = _lib.rnnt_b200_add_joint_loss(trans.data_ptr(), pred.data_ptr(),
+                                           dtrans.data_ptr() if dtrans is not None else None,
+                                           dpred.data_ptr() if dpred is not None else None,
+                                           lab, label_lens.data_ptr(), act_lens.data_ptr(), V, N,
+                                           costs.data_ptr(), scale, ws.data_ptr(), opt)
+    if st != 0:
+        raise RuntimeError("rnnt_b200_add_joint_loss failed: " + warp_rnnt.status_string(st))
+    return ws
+
+
+class _AddJointRNNT(Function):
+    @staticmethod
+    def forward(ctx, trans, pred, labels, act_lens, label_lens, blank, reduction):
+        certify_joint_inputs(trans, pred, labels, act_lens, label_lens)
+        if not trans.is_cuda:
+            raise RuntimeError("warprnnt_pytorch (B200 build) runs on CUDA tensors only")
+        if reduction not in ('none', 'sum', 'mean'):
+            raise ValueError("reduction must be 'none', 'sum' or 'mean'")
+        N = trans.size(0)
+        need = trans.requires_grad or pred.requires_grad
+        costs = torch.empty(N, dtype=torch.float32, device=trans.device)
+        dtrans = torch.empty_like(trans) if need else None
+        dpred = torch.empty_like(pred) if need else None
+        scale = 1.0 / N if reduction == 'mean' else 1.0
+        ctx.ws = add_joint_call(trans, pred, labels, act_lens, label_lens, costs, dtrans, dpred, blank, scale)
+        ctx.grads = (dtrans, dpred)
+        if reduction in ('sum', 'mean'):
+            costs = costs.sum().unsqueeze_(-1)
+            if reduction == 'mean':
+                costs /= N
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        dtrans, dpred = ctx.grads
+        go = grad_output.reshape(-1, 1, 1).to(dtrans)     # [1,1,1] or [N,1,1]; the factors are small
+        return dtrans * go, dpred * go, None, None, None, None, None
+
+
+def add_joint_rnnt_loss(trans, pred, labels, act_lens, label_lens, blank=0, reduction='mean'):
+    return _AddJointRNNT.apply(trans, pred, labels, act_lens, label_lens, blank, reduction)
+
+
+class AddJointRNNTLoss(Module):
+    def __init__(self, blank=0, reduction='mean'):
+        super().__init__()
+        self.blank, self.reduction = blank, reduction
+
+    def forward(self, trans, pred, labels, act_lens, label_lens):
+        return _AddJointRNNT.apply(trans, pred, labels, act_lens, label_lens, self.blank, self.reduction)
