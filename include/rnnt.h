@@ -218,6 +218,17 @@ rnntStatus_t rnnt_b200_add_joint_loss(const float* trans, const float* pred, flo
                                       float grad_scale, void* workspace, struct rnntOptions options);
 rnntStatus_t rnnt_b200_add_joint_workspace_size(int maxT, int maxU, int minibatch, int alphabet_size,
                                                 size_t* size_bytes);
+/* Training-step split of the same (see rnnt_b200_forward / rnnt_b200_backward): the backward half
+ * folds grad_costs_device[b] * grad_scale into the factor gradients. */
+rnntStatus_t rnnt_b200_add_joint_forward(const float* trans, const float* pred, const int* flat_labels,
+                                         const int* label_lengths, const int* input_lengths,
+                                         int alphabet_size, int minibatch, float* costs_device,
+                                         int prepare_backward, void* workspace, struct rnntOptions options);
+rnntStatus_t rnnt_b200_add_joint_backward(const float* trans, const float* pred, float* grad_trans,
+                                          float* grad_pred, const int* flat_labels,
+                                          const int* label_lengths, const int* input_lengths,
+                                          int alphabet_size, int minibatch, const float* grad_costs_device,
+                                          float grad_scale, void* workspace, struct rnntOptions options);
 
 /* Number of kernels the last compute call on this thread launched (bench.py's gpu_launches). */
 int rnnt_b200_last_launch_count(void);

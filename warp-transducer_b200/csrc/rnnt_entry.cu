@@ -464,8 +464,10 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
 }
 
 // ---- additive-joint variant (rnnt_joint.cuh) ----------------------------------------------------
+constexpr int kJointSlices = 16;  // max split-K slabs of the S = Ef.Eg^T contraction (K = V is the long axis)
+inline int joint_slices(int V) { return std::max(1, std::min(kJointSlices, V / 320)); }
 struct JointWorkspace {
-    float *ef, *eg, *mf, *mg, *inv_s, *wm, *bk, *lb;
+    float *ef, *eg, *mf, *mg, *inv_s, *wm, *bk, *lb, *part;
     float2* lp2;
     double *alphas, *betas, *llf, *llb;
     size_t bytes;
@@ -488,6 +490,7 @@ JointWorkspace carve_joint(void* base, int N, int T, int U, int V) {
     w.wm = static_cast<float*>(take(C * 4));
     w.bk = static_cast<float*>(take(C * 4));
     w.lb = static_cast<float*>(take(C * 4));
+    w.part = static_cast<float*>(take(C * 4 * kJointSlices));
     w.lp2 = static_cast<float2*>(take(D * 8));
     w.alphas = static_cast<double*>(take(D * 8));
     w.betas = static_cast<double*>(take(D * 8));
@@ -499,9 +502,11 @@ JointWorkspace carve_joint(void* base, int N, int T, int U, int V) {
 
 rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG, const int* labels,
                            const int* ylen, const int* xlen, int V, int N, float* costs, float scale,
-                           void* workspace, rnntOptions opt) {
-    if (!f || !g || !labels || !ylen || !xlen || !costs || !workspace || V <= 0 || N <= 0 ||
-        opt.maxT <= 0 || opt.maxU <= 0 || (dF == nullptr) != (dG == nullptr))
+                           const float* scale_vec, Phase phase, bool want_beta, void* workspace,
+                           rnntOptions opt) {
+    if (!f || !g || !labels || !ylen || !xlen || (!costs && phase != kBackward) || !workspace || V <= 0 ||
+        N <= 0 || opt.maxT <= 0 || opt.maxU <= 0 || (dF == nullptr) != (dG == nullptr) ||
+        (phase == kBackward && !dF))
         return RNNT_STATUS_INVALID_VALUE;
     if (opt.loc != RNNT_GPU) return opt.loc == RNNT_CPU ? RNNT_STATUS_EXECUTION_FAILED : RNNT_STATUS_INVALID_VALUE;
     const int T = opt.maxT, U = opt.maxU;
@@ -521,22 +526,33 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     d.rows = (uint32_t)rows64;
     d.divU = FastDiv(U);
     d.divT = FastDiv(T);
-    const bool want_grad = dF != nullptr;
+    const bool want_grad = dF != nullptr && phase != kForward;
+    const bool with_beta = dF != nullptr || want_beta;
 
+    if (phase != kBackward) {
     // J1: factor-wise max and exponentials
     joint_prep_kernel<<<(N * T + 7) / 8, 256, 0, s>>>(f, w.ef, w.mf, N * T, V);
     joint_prep_kernel<<<(N * U + 7) / 8, 256, 0, s>>>(g, w.eg, w.mg, N * U, V);
-    // J2: S = Ef . Eg^T  -> lse, lattice log-prob pairs
+    // J2: S = Ef . Eg^T in kJointSlices deterministic K-slabs, then lse + lattice log-prob pairs
     {
         Operand A{w.ef, (size_t)T * V, V, 1}, B{w.eg, (size_t)U * V, V, 1};
+        const int slices = joint_slices(V);
+        dim3 grid((U + 63) / 64, (T + 63) / 64, N * slices);
+        if (U <= 32) {
+            grid.x = (U + 31) / 32;
+            joint_gemm_kernel<EpiPartial, 32, 32><<<grid, 256, 0, s>>>(
+                A, B, T, U, V, slices, EpiPartial{w.part, (size_t)rows64, T, U, slices});
+        } else {
+            joint_gemm_kernel<EpiPartial, 64, 32><<<grid, 256, 0, s>>>(
+                A, B, T, U, V, slices, EpiPartial{w.part, (size_t)rows64, T, U, slices});
+        }
         EpiStats epi{f, g, w.mf, w.mg, labels, xlen, ylen, w.inv_s, w.lp2, jd, d};
-        dim3 grid((U + 63) / 64, (T + 63) / 64, N);
-        joint_gemm_kernel<<<grid, 256, 0, s>>>(A, B, T, U, V, epi);
+        joint_stats_kernel<<<(d.rows + 255) / 256, 256, 0, s>>>(w.part, slices, epi);
     }
     // lattice (same kernel as the dense path)
     {
         const int threads = (U + 31) / 32 * 32;
-        dim3 grid(N, want_grad ? 2 : 1);
+        dim3 grid(N, with_beta ? 2 : 1);
         const size_t ring = (size_t)kRing * threads * sizeof(float2);
         auto launch = [&](auto kernel) {
             static thread_local size_t opted = 0;
@@ -549,19 +565,31 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
         if (threads > 32) launch(lattice_kernel<float, true>);
         else launch(lattice_kernel<float, false>);
     }
-    g_last_launches += 4;
+    g_last_launches += 5;
+    }  // phase != kBackward
     if (want_grad) {
         joint_weights_kernel<<<(d.rows + 255) / 256, 256, 0, s>>>(w.lp2, w.alphas, w.betas, w.llf, w.inv_s,
-                                                                 xlen, ylen, w.wm, w.bk, w.lb, scale, d);
-        {   // dF = Ef (.) (Wm . Eg)
-            Operand A{w.wm, (size_t)T * U, U, 1}, B{w.eg, (size_t)U * V, 1, V};
-            dim3 grid((V + 63) / 64, (T + 63) / 64, N);
-            joint_gemm_kernel<<<grid, 256, 0, s>>>(A, B, T, V, U, EpiGrad{w.ef, dF, T, V});
-        }
-        {   // dG = Eg (.) (Wm^T . Ef)
-            Operand A{w.wm, (size_t)T * U, 1, U}, B{w.ef, (size_t)T * V, 1, V};
-            dim3 grid((V + 63) / 64, (U + 63) / 64, N);
-            joint_gemm_kernel<<<grid, 256, 0, s>>>(A, B, U, V, T, EpiGrad{w.eg, dG, U, V});
+                                                                 xlen, ylen, w.wm, w.bk, w.lb, scale, scale_vec, d);
+        if (V >= 512) {  // long vocabulary: one thread per column, thin contraction
+            {   // dF[t,v] = Ef[t,v] * sum_u Wm[t,u] Eg[u,v]
+                dim3 grid((V + 255) / 256, (T + kJointRT - 1) / kJointRT, N);
+                joint_thin_kernel<<<grid, 256, 0, s>>>(w.wm, U, 1, (size_t)T * U, w.eg, w.ef, dF, T, U, V);
+            }
+            {   // dG[u,v] = Eg[u,v] * sum_t Wm[t,u] Ef[t,v]
+                dim3 grid((V + 255) / 256, (U + kJointRT - 1) / kJointRT, N);
+                joint_thin_kernel<<<grid, 256, 0, s>>>(w.wm, 1, U, (size_t)T * U, w.ef, w.eg, dG, U, T, V);
+            }
+        } else {  // short vocabulary: tiled GEMM
+            {
+                Operand A{w.wm, (size_t)T * U, U, 1}, B{w.eg, (size_t)U * V, 1, V};
+                dim3 grid((V + 63) / 64, (T + 63) / 64, N);
+                joint_gemm_kernel<EpiGrad><<<grid, 256, 0, s>>>(A, B, T, V, U, 1, EpiGrad{w.ef, dF, T, V});
+            }
+            {
+                Operand A{w.wm, (size_t)T * U, 1, U}, B{w.ef, (size_t)T * V, 1, V};
+                dim3 grid((V + 63) / 64, (U + 63) / 64, N);
+                joint_gemm_kernel<EpiGrad><<<grid, 256, 0, s>>>(A, B, U, V, T, 1, EpiGrad{w.eg, dG, U, V});
+            }
         }
         joint_sparse_f_kernel<<<(N * T + 127) / 128, 128, 0, s>>>(dF, w.bk, w.lb, labels, ylen, jd);
         joint_sparse_g_kernel<<<(N * U + 127) / 128, 128, 0, s>>>(dG, w.bk, w.lb, labels, xlen, ylen, jd);
@@ -720,7 +748,27 @@ rnntStatus_t rnnt_b200_add_joint_loss(const float* trans, const float* pred, flo
                                       int alphabet_size, int minibatch, float* costs_device,
                                       float grad_scale, void* workspace, rnntOptions options) {
     return run_add_joint(trans, pred, grad_trans, grad_pred, flat_labels, label_lengths, input_lengths,
-                         alphabet_size, minibatch, costs_device, grad_scale, workspace, options);
+                         alphabet_size, minibatch, costs_device, grad_scale, nullptr, kFull, false, workspace,
+                         options);
+}
+
+rnntStatus_t rnnt_b200_add_joint_forward(const float* trans, const float* pred, const int* flat_labels,
+                                         const int* label_lengths, const int* input_lengths,
+                                         int alphabet_size, int minibatch, float* costs_device,
+                                         int prepare_backward, void* workspace, rnntOptions options) {
+    return run_add_joint(trans, pred, nullptr, nullptr, flat_labels, label_lengths, input_lengths,
+                         alphabet_size, minibatch, costs_device, 1.0f, nullptr, kForward,
+                         prepare_backward != 0, workspace, options);
+}
+
+rnntStatus_t rnnt_b200_add_joint_backward(const float* trans, const float* pred, float* grad_trans,
+                                          float* grad_pred, const int* flat_labels,
+                                          const int* label_lengths, const int* input_lengths,
+                                          int alphabet_size, int minibatch, const float* grad_costs_device,
+                                          float grad_scale, void* workspace, rnntOptions options) {
+    return run_add_joint(trans, pred, grad_trans, grad_pred, flat_labels, label_lengths, input_lengths,
+                         alphabet_size, minibatch, nullptr, grad_scale, grad_costs_device, kBackward, false,
+                         workspace, options);
 }
 
 rnntStatus_t rnnt_b200_add_joint_workspace_size(int maxT, int maxU, int minibatch, int alphabet_size,

@@ -52,51 +52,70 @@ struct Operand {
     int s_k;       // stride of the k index
 };
 
-template <typename Epi>
+template <typename Epi, int TN = 64, int KC = 16>
 __global__ void __launch_bounds__(256)
-joint_gemm_kernel(Operand A, Operand B, int M, int Nn, int K, Epi epi) {
-    __shared__ float sa[16][64 + 1], sb[16][64 + 1];
-    const int b = blockIdx.z;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+joint_gemm_kernel(Operand A, Operand B, int M, int Nn, int Kfull, int slices, Epi epi) {
+    // 64 x TN output tile (TN = 32 for skinny right-hand sides), KC-deep k-chunks
+    constexpr int PN = TN / 16;  // output columns per thread
+    __shared__ float sa[KC][64 + 1], sb[KC][TN + 1];
+    // blockIdx.z = batch * slices + k-slice; each slice covers a KC-aligned range of K
+    const int b = blockIdx.z / slices, ks = blockIdx.z - b * slices;
+    const int kper = ((Kfull + slices - 1) / slices + KC - 1) / KC * KC;
+    const int kbeg = ks * kper;
+    const int K = min(Kfull, kbeg + kper);
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * TN;
     const float* a = A.p + (size_t)b * A.batch;
     const float* bb = B.p + (size_t)b * B.batch;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4x4 outputs each
-    float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        // cooperative loads: 64x16 of A and of B, 4 elements per thread each
-        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-            // two index orders so that whichever stride is 1 gives coalesced reads
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x PN outputs each
+    float acc[4][PN] = {};
+    for (int k0 = kbeg; k0 < K; k0 += KC) {
+        // cooperative loads; the index order follows whichever stride is 1 so reads coalesce
+        for (int i = threadIdx.x; i < 64 * KC; i += 256) {
             int r, kk;
-            if (A.s_k == 1) { kk = i & 15; r = i >> 4; } else { r = i & 63; kk = i >> 6; }
+            if (A.s_k == 1) { kk = i % KC; r = i / KC; } else { r = i & 63; kk = i >> 6; }
             const int m = m0 + r, k = k0 + kk;
             sa[kk][r] = (m < M && k < K) ? __ldg(a + (size_t)m * A.s_outer + (size_t)k * A.s_k) : 0.0f;
-            if (B.s_k == 1) { kk = i & 15; r = i >> 4; } else { r = i & 63; kk = i >> 6; }
-            const int n = n0 + r, k2 = k0 + kk;
-            sb[kk][r] = (n < Nn && k2 < K) ? __ldg(bb + (size_t)n * B.s_outer + (size_t)k2 * B.s_k) : 0.0f;
+        }
+        for (int i = threadIdx.x; i < TN * KC; i += 256) {
+            int r, kk;
+            if (B.s_k == 1) { kk = i % KC; r = i / KC; } else { r = i % TN; kk = i / TN; }
+            const int n = n0 + r, k = k0 + kk;
+            sb[kk][r] = (n < Nn && k < K) ? __ldg(bb + (size_t)n * B.s_outer + (size_t)k * B.s_k) : 0.0f;
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float av[4], bv[4];
+        for (int kk = 0; kk < KC; ++kk) {
+            float av[4], bv[PN];
 #pragma unroll
             for (int i = 0; i < 4; ++i) av[i] = sa[kk][ty * 4 + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = sb[kk][tx * 4 + j];
+            for (int j = 0; j < PN; ++j) bv[j] = sb[kk][tx * PN + j];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < PN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
-            if (m < M && n < Nn) epi(b, m, n, acc[i][j]);
+        for (int j = 0; j < PN; ++j) {
+            const int m = m0 + ty * 4 + i, n = n0 + tx * PN + j;
+            if (m < M && n < Nn) epi(blockIdx.z, m, n, acc[i][j]);
         }
 }
+
+// ---- J2: split-K partial sums (deterministic: one slab per K-slice, summed in fixed order) ---------
+struct EpiPartial {
+    float* part;  // [slices][N,T,U]
+    size_t cells; // N*T*U
+    int T, U, slices;
+    __device__ void operator()(int bz, int t, int u, float acc) const {
+        const int b = bz / slices, ks = bz - b * slices;
+        part[(size_t)ks * cells + ((size_t)b * T + t) * U + u] = acc;
+    }
+};
 
 // ---- J2 epilogue: S -> lse, lattice log-prob pair (diagonal-major), keep 1/S -----------------------
 struct EpiStats {
@@ -130,6 +149,18 @@ struct EpiStats {
     }
 };
 
+__global__ void __launch_bounds__(256)
+joint_stats_kernel(const float* __restrict__ part, int slices, const EpiStats epi) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= epi.d.rows) return;
+    uint32_t bt, u, b, t;
+    epi.d.divU.divmod(r, bt, u);
+    epi.d.divT.divmod(bt, b, t);
+    float S = 0.0f;
+    for (int ks = 0; ks < slices; ++ks) S += part[(size_t)ks * epi.d.rows + r];
+    epi((int)b, (int)t, (int)u, S);
+}
+
 // ---- J3: per cell weights from the lattices ---------------------------------------------------------
 //   Wm = e^{alpha+beta-ll} / S ;  Bk = blank-transition occupancy ;  Lb = label-transition occupancy
 __global__ void __launch_bounds__(256)
@@ -137,7 +168,8 @@ joint_weights_kernel(const float2* __restrict__ lp2, const double* __restrict__ 
                      const double* __restrict__ betas, const double* __restrict__ llf,
                      const float* __restrict__ inv_s, const int* __restrict__ xlen,
                      const int* __restrict__ ylen, float* __restrict__ Wm, float* __restrict__ Bk,
-                     float* __restrict__ Lb, const float scale, const Dims d) {
+                     float* __restrict__ Lb, const float scale_in, const float* __restrict__ scale_vec,
+                     const Dims d) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= d.rows) return;
     uint32_t bt, u, b, t;
@@ -146,6 +178,7 @@ joint_weights_kernel(const float2* __restrict__ lp2, const double* __restrict__ 
     int Tb, Ub;
     utt_extent(d, xlen, ylen, b, Tb, Ub);
     float w = 0.0f, bk = 0.0f, lb = 0.0f;
+    const float scale = scale_vec ? scale_in * __ldg(scale_vec + b) : scale_in;
     if ((int)t < Tb && (int)u < Ub) {
         const size_t q = skew(d, b, t, u);
         const float2 lp = lp2[q];
@@ -160,7 +193,54 @@ joint_weights_kernel(const float2* __restrict__ lp2, const double* __restrict__ 
     Lb[r] = lb;
 }
 
-// ---- J4/J5 epilogue: multiply by the factor's own exponentials -------------------------------------
+// ---- J4/J5: out[b,r,v] = Eout[b,r,v] * sum_s W(r,s) * Ein[b,s,v]  (thin contraction over s) ----------
+//   dF: r = t, s = u, W(r,s) = Wm[b,t,u], Ein = Eg, Eout = Ef
+//   dG: r = u, s = t, W(r,s) = Wm[b,t,u] (transposed access), Ein = Ef, Eout = Eg
+// One thread per vocabulary column (coalesced over v), RT output rows per block held in registers,
+// the W tile broadcast from shared memory: RT FMAs per 4-byte load of Ein.
+constexpr int kJointRT = 16, kJointSC = 64;
+__global__ void __launch_bounds__(256)
+joint_thin_kernel(const float* __restrict__ Wm, int w_stride_r, int w_stride_s, size_t w_batch,
+                  const float* __restrict__ Ein, const float* __restrict__ Eout, float* __restrict__ out,
+                  int R, int S, int V) {
+    __shared__ float sw[kJointSC][kJointRT];
+    const int b = blockIdx.z, r0 = blockIdx.y * kJointRT;
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    const float* w = Wm + (size_t)b * w_batch;
+    const float* ein = Ein + (size_t)b * S * V;
+    float acc[kJointRT];
+#pragma unroll
+    for (int i = 0; i < kJointRT; ++i) acc[i] = 0.0f;
+    for (int s0 = 0; s0 < S; s0 += kJointSC) {
+        for (int i = threadIdx.x; i < kJointSC * kJointRT; i += 256) {
+            const int ss = i / kJointRT, rr = i % kJointRT;
+            const int s = s0 + ss, r = r0 + rr;
+            sw[ss][rr] = (s < S && r < R) ? __ldg(w + (size_t)r * w_stride_r + (size_t)s * w_stride_s) : 0.0f;
+        }
+        __syncthreads();
+        if (v < V) {
+            const int smax = min(kJointSC, S - s0);
+            for (int ss = 0; ss < smax; ++ss) {
+                const float e = __ldg(ein + (size_t)(s0 + ss) * V + v);
+#pragma unroll
+                for (int i = 0; i < kJointRT; ++i) acc[i] = fmaf(sw[ss][i], e, acc[i]);
+            }
+        }
+        __syncthreads();
+    }
+    if (v < V) {
+#pragma unroll
+        for (int i = 0; i < kJointRT; ++i) {
+            const int r = r0 + i;
+            if (r < R) {
+                const size_t o = ((size_t)b * R + r) * V + v;
+                out[o] = __ldg(Eout + o) * acc[i];
+            }
+        }
+    }
+}
+
+// generic-GEMM form of the same products, used when V is too short to give every thread a column
 struct EpiGrad {
     const float* e;  // Ef [N,T,V] (or Eg [N,U,V])
     float* out;      // dF (or dG), same shape

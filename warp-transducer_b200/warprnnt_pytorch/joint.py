@@ -22,6 +22,12 @@ _P = C.c_void_p
 _lib.rnnt_b200_add_joint_loss.restype = C.c_int
 _lib.rnnt_b200_add_joint_loss.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P,
                                           warp_rnnt.rnntOptions]
+_lib.rnnt_b200_add_joint_forward.restype = C.c_int
+_lib.rnnt_b200_add_joint_forward.argtypes = [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P,
+                                             warp_rnnt.rnntOptions]
+_lib.rnnt_b200_add_joint_backward.restype = C.c_int
+_lib.rnnt_b200_add_joint_backward.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P,
+                                              warp_rnnt.rnntOptions]
 _lib.rnnt_b200_add_joint_workspace_size.restype = C.c_int
 _lib.rnnt_b200_add_joint_workspace_size.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
 
@@ -73,7 +79,20 @@ def add_joint_call(trans, pred, labels, act_lens, label_lens, costs, dtrans, dpr
     return ws
 
 
+def _joint_opts(trans, pred, blank):
+    return warp_rnnt.rnntOptions(loc=1, num_threads=0,
+                                 stream=torch.cuda.current_stream(trans.device).cuda_stream,
+                                 blank_label=blank, maxT=trans.shape[1], maxU=pred.shape[1], batch_first=True)
+
+
+def _lab_ptr(labels):
+    return labels.data_ptr() if labels.numel() else labels.new_zeros(1).data_ptr()
+
+
 class _AddJointRNNT(Function):
+    """forward: factor exponentials, S = Ef.Eg^T, alpha/beta lattices, costs.  backward: weights +
+    the two factor-gradient contractions with grad_output[b] and the reduction factor folded in."""
+
     @staticmethod
     def forward(ctx, trans, pred, labels, act_lens, label_lens, blank, reduction):
         certify_joint_inputs(trans, pred, labels, act_lens, label_lens)
@@ -81,14 +100,24 @@ class _AddJointRNNT(Function):
             raise RuntimeError("warprnnt_pytorch (B200 build) runs on CUDA tensors only")
         if reduction not in ('none', 'sum', 'mean'):
             raise ValueError("reduction must be 'none', 'sum' or 'mean'")
-        N = trans.size(0)
+        N, T, V = trans.shape
+        U = pred.shape[1]
         need = trans.requires_grad or pred.requires_grad
         costs = torch.empty(N, dtype=torch.float32, device=trans.device)
-        dtrans = torch.empty_like(trans) if need else None
-        dpred = torch.empty_like(pred) if need else None
-        scale = 1.0 / N if reduction == 'mean' else 1.0
-        ctx.ws = add_joint_call(trans, pred, labels, act_lens, label_lens, costs, dtrans, dpred, blank, scale)
-        ctx.grads = (dtrans, dpred)
+        n = C.c_size_t(0)
+        _lib.rnnt_b200_add_joint_workspace_size(T, U, N, V, C.byref(n))
+        with torch.cuda.device(trans.device):
+            ws = torch.empty(n.value, dtype=torch.uint8, device=trans.device)
+            st = _lib.rnnt_b200_add_joint_forward(trans.data_ptr(), pred.data_ptr(), _lab_ptr(labels),
+                                                  label_lens.data_ptr(), act_lens.data_ptr(), V, N,
+                                                  costs.data_ptr(), 1 if need else 0, ws.data_ptr(),
+                                                  _joint_opts(trans, pred, blank))
+        if st != 0:
+            raise RuntimeError("rnnt_b200_add_joint_forward failed: " + warp_rnnt.status_string(st))
+        if need:
+            ctx.save_for_backward(trans, pred, labels, act_lens, label_lens)
+            ctx.ws, ctx.blank = ws, blank
+            ctx.scale = 1.0 / N if reduction == 'mean' else 1.0
         if reduction in ('sum', 'mean'):
             costs = costs.sum().unsqueeze_(-1)
             if reduction == 'mean':
@@ -97,9 +126,19 @@ class _AddJointRNNT(Function):
 
     @staticmethod
     def backward(ctx, grad_output):
-        dtrans, dpred = ctx.grads
-        go = grad_output.reshape(-1, 1, 1).to(dtrans)     # [1,1,1] or [N,1,1]; the factors are small
-        return dtrans * go, dpred * go, None, None, None, None, None
+        trans, pred, labels, act_lens, label_lens = ctx.saved_tensors
+        N, T, V = trans.shape
+        g = grad_output.reshape(-1).to(device=trans.device, dtype=torch.float32)
+        g = g.expand(N).contiguous() if g.numel() == 1 else g.contiguous()
+        dtrans, dpred = torch.empty_like(trans), torch.empty_like(pred)
+        with torch.cuda.device(trans.device):
+            st = _lib.rnnt_b200_add_joint_backward(trans.data_ptr(), pred.data_ptr(), dtrans.data_ptr(),
+                                                   dpred.data_ptr(), _lab_ptr(labels), label_lens.data_ptr(),
+                                                   act_lens.data_ptr(), V, N, g.data_ptr(), ctx.scale,
+                                                   ctx.ws.data_ptr(), _joint_opts(trans, pred, ctx.blank))
+        if st != 0:
+            raise RuntimeError("rnnt_b200_add_joint_backward failed: " + warp_rnnt.status_string(st))
+        return dtrans, dpred, None, None, None, None, None
 
 
 def add_joint_rnnt_loss(trans, pred, labels, act_lens, label_lens, blank=0, reduction='mean'):
