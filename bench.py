@@ -165,7 +165,9 @@ def time_cpu(V, T, L, threads, target_s, max_utt):
     step()
     per_utt = (time.perf_counter() - t0) / pilot_n
     n = int(max(pilot_n, min(max_utt, target_s / max(per_utt, 1e-9))))
-    n = min(n, max_utt)
+    # the reference parallelises over utterances (cpu_rnnt.h:290 `#pragma omp parallel for`): a sample
+    # smaller than the core count would leave cores idle and understate the CPU
+    n = min(max(n, threads), max_utt)
     step, kind = cpu_reference_step_fn(V, T, L, n, threads)
     step()
     return step, kind, n
