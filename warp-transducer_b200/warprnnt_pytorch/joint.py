@@ -15,7 +15,8 @@ import torch
 from torch.autograd import Function
 from torch.nn import Module
 
-from . import check_contiguous, check_dim, check_type, warp_rnnt
+from . import warp_rnnt
+from ._checks import check_contiguous, check_dim, check_type
 
 _lib = warp_rnnt.lib()
 _P = C.c_void_p
