@@ -165,9 +165,10 @@ def time_cpu(V, T, L, threads, target_s, max_utt):
     step()
     per_utt = (time.perf_counter() - t0) / pilot_n
     n = int(max(pilot_n, min(max_utt, target_s / max(per_utt, 1e-9))))
-    # the reference parallelises over utterances (cpu_rnnt.h:290 `#pragma omp parallel for`): a sample
-    # smaller than the core count would leave cores idle and understate the CPU
-    n = min(max(n, threads), max_utt)
+    # the reference parallelises over utterances (cpu_rnnt.h:290 `#pragma omp parallel for`), so a tiny
+    # sample would leave cores idle and understate the CPU; measured on the 128-core GPU box the rate
+    # is flat from 40 utterances up (11.4 @40, 11.9 @128 utt/s), so 32 is the floor
+    n = min(max(n, min(32, threads)), max_utt)
     step, kind = cpu_reference_step_fn(V, T, L, n, threads)
     step()
     return step, kind, n
@@ -179,7 +180,8 @@ def run_reference_arm(args):
         return
     N, T, L, V = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    step, kind, n = time_cpu(V, T, L, cores, target_s=1.5, max_utt=N)
+    # size the per-step sample so that the whole --steps/--warmup run stays within ~2.5 minutes
+    step, kind, n = time_cpu(V, T, L, cores, target_s=150.0 / (args.steps + args.warmup), max_utt=N)
     for _ in range(max(args.warmup - 1, 0)):
         step()
     t0 = time.perf_counter()

@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.join(ROOT, "warp-transducer_b200"))
 import warprnnt_pytorch.warp_rnnt as wr  # noqa: E402
 
 CFG = {"c2": (128, 150, 40, 28), "c3": (128, 150, 20, 5000), "c4": (64, 1500, 300, 50),
-       "c5": (128, 200, 40, 5000)}
+       "c5": (128, 200, 40, 5000), "c3odd": (128, 150, 20, 5001), "c3v2": (128, 150, 20, 5002),
+       "v1025": (64, 150, 40, 1025), "v4097": (64, 150, 40, 4097)}
 
 
 def main():
