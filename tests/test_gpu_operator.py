@@ -256,3 +256,44 @@ def test_sixteen_bit_storage(dtype):
         wr.gpu_rnnt_async(acts.detach(), labels, tl, ul, c2, g2, 0)
         torch.cuda.synchronize()
         assert torch.equal(g2, acts.grad) and torch.equal(c2, out.detach())
+
+
+def test_concurrent_host_threads():
+    """The library keeps no shared mutable state (per-thread launch counters / event pools / side
+    streams, caller-owned workspace): four host threads on four streams, different shapes."""
+    import threading
+    from warprnnt_pytorch import warp_rnnt as wr
+    shapes = [(3, 11, 5, 28), (2, 9, 40, 6), (2, 6, 4, 1028), (4, 30, 8, 50)]
+    results, errors = {}, []
+
+    def work(idx, shape):
+        try:
+            N, T, U, V = shape
+            rng = np.random.default_rng(100 + idx)
+            acts_np = rng.standard_normal((N, T, U, V)).astype(np.float32)
+            labels_np = rng.integers(1, V, size=(N, U - 1)).astype(np.int32)
+            tl_np = rng.integers(T // 2 + 1, T + 1, size=N).astype(np.int32)
+            ul_np = rng.integers(0, U, size=N).astype(np.int32)
+            c_ref, g_ref, _ = pyoracle.rnnt_logits(acts_np.astype(np.float64), labels_np, tl_np, ul_np, 0, threads=1)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                acts = torch.tensor(acts_np, device="cuda")
+                labels, tl, ul = (torch.as_tensor(x).cuda() for x in (labels_np, tl_np, ul_np))
+                costs, grads = torch.empty(N, device="cuda"), torch.empty_like(acts)
+                for _ in range(25):
+                    grads.fill_(float("nan"))
+                    wr.gpu_rnnt_async(acts, labels, tl, ul, costs, grads, 0)
+                stream.synchronize()
+            ok = np.allclose(costs.cpu().numpy(), c_ref, rtol=1e-5) and \
+                np.allclose(grads.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)
+            results[idx] = ok
+        except Exception as ex:      # surfaced in the main thread below
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=work, args=(i, s)) for i, s in enumerate(shapes)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert all(results.get(i) for i in range(len(shapes))), results
