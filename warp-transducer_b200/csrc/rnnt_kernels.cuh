@@ -145,7 +145,10 @@ rowstats_row_kernel(const IO* __restrict__ acts, const int* __restrict__ labels,
 // Small LPR keeps the per-row bookkeeping (index decode, length checks, lattice stores) off most
 // lanes: at V=28 two lanes own a row, at V=50 (float2) four do.
 // =================================================================================================
-constexpr int kVPL = 8;
+#ifndef RNNT_VPL
+#define RNNT_VPL 8
+#endif
+constexpr int kVPL = RNNT_VPL;
 
 template <typename T, int VEC, int LPR, typename IO = T>
 __global__ void __launch_bounds__(256)
