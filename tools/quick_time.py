@@ -10,12 +10,15 @@ sys.path.insert(0, os.path.join(ROOT, "warp-transducer_b200"))
 import warprnnt_pytorch.warp_rnnt as wr  # noqa: E402
 
 CFG = {"c2": (128, 150, 40, 28), "c3": (128, 150, 20, 5000), "c4": (64, 1500, 300, 50),
-       "c5": (128, 200, 40, 5000), "c3odd": (128, 150, 20, 5001), "c3v2": (128, 150, 20, 5002),
+       "c5": (128, 200, 40, 5000), "c3h": (64, 150, 20, 5000), "c3odd": (128, 150, 20, 5001), "c3v2": (128, 150, 20, 5002),
        "v1025": (64, 150, 40, 1025), "v4097": (64, 150, 40, 4097)}
 
 
 def main():
     dt = torch.float32
+    if "--fp64" in sys.argv:
+        sys.argv.remove("--fp64")
+        dt = torch.float64
     if "--bf16" in sys.argv:
         sys.argv.remove("--bf16")
         dt = torch.bfloat16
@@ -31,7 +34,7 @@ def main():
         labels = torch.as_tensor(rng.integers(1, V, size=(N, L)).astype(np.int32)).to(dev)
         tl = torch.full((N,), T, dtype=torch.int32, device=dev)
         ul = torch.full((N,), L, dtype=torch.int32, device=dev)
-        costs = torch.empty(N, device=dev)
+        costs = torch.empty(N, device=dev, dtype=torch.float64 if dt == torch.float64 else torch.float32)
         ws = None
         for mode, g in (("loss+grad", grads), ("loss", None)):
             ts = []
