@@ -166,6 +166,8 @@ SHAPES = [
     (2, 3, 2, 301, 0),     # scalar, 2 per thread, partial second slot
     (4, 20, 33, 6, 0),     # U > 32: multi-warp lattice
     (2, 9, 70, 4, 0),      # 3 warps
+    (1, 3, 800, 4, 0),     # 25 warps: cp.async ring above 48 KB (shared-memory opt-in)
+    (1, 2, 1024, 3, 0),    # the maximum label extent (same limit as the reference's launch)
     (3, 40, 1, 6, 0),      # U == 1: empty label sequences
     (3, 1, 5, 6, 0),       # T == 1
     (1, 1, 1, 4, 0),       # single cell

@@ -376,11 +376,10 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         dim3 grid(g.d.N, with_beta ? 2 : 1);
         const size_t ring = (size_t)kRing * threads * sizeof(Pair);
         auto launch = [&](auto kernel) {
-            static thread_local size_t opted = 0;
-            if (ring > 48 * 1024 && ring > opted) {
+            // opt-in for rings above 48 KB (maxU > 768); set unconditionally when needed: the
+            // attribute is per device and the call is rare and cheap next to a >768-thread wavefront
+            if (ring > 48 * 1024)
                 cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
-                opted = ring;
-            }
             kernel<<<grid, threads, ring, st>>>(static_cast<const Pair*>(g.w.lp2), g.xlen, g.ylen,
                                                g.w.alphas, g.w.betas, g.w.llf, g.w.llb, g.costs, g.d);
         };
@@ -555,11 +554,10 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
         dim3 grid(N, with_beta ? 2 : 1);
         const size_t ring = (size_t)kRing * threads * sizeof(float2);
         auto launch = [&](auto kernel) {
-            static thread_local size_t opted = 0;
-            if (ring > 48 * 1024 && ring > opted) {
+            // opt-in for rings above 48 KB (maxU > 768); set unconditionally when needed: the
+            // attribute is per device and the call is rare and cheap next to a >768-thread wavefront
+            if (ring > 48 * 1024)
                 cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
-                opted = ring;
-            }
             kernel<<<grid, threads, ring, s>>>(w.lp2, xlen, ylen, w.alphas, w.betas, w.llf, w.llb, costs, d);
         };
         if (threads > 32) launch(lattice_kernel<float, true>);
