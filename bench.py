@@ -15,7 +15,7 @@ value      device-resident: inputs already in HBM, compute_rnnt_loss_async + los
            K steps between CUDA events, max over ranks.
 e2e        through the reference-facing C-ABI call compute_rnnt_loss() with the step's inputs
            copied from pinned host memory inside the timed region and the costs landing on the host.
-roofline   the dominant kernel (grad_kernel, 8 B/element algorithmic) timed with CUDA events on the
+roofline   the dominant kernel (grad_row_kernel, 8 B/element algorithmic) timed with CUDA events on the
            library's own stream during the timed steps, against MEASURED_PEAKS.json.
 cpu_baseline  the reference's CPU path (oracle/_ref, else the oracle port) on a bounded sample.
 """
@@ -377,13 +377,13 @@ def run_b200_arm(args):
     grad_ms, rows_ms, lat_ms = float(kms[2]), float(kms[0]), float(kms[1])
     achieved = 8.0 * E / (grad_ms * 1e-3) / 1e9 if grad_ms > 0 else None
     roofline = {
-        "bound": "hbm", "kernel": "grad_kernel (pass 2: read logits 4 B + write gradient 4 B per element)",
+        "bound": "hbm", "kernel": "grad_row_kernel (pass 2: read logits 4 B + write gradient 4 B per element)",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": achieved / peaks["hbm_gbs"] if achieved else None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
         "traffic": None, "ms_per_launch": grad_ms,
         "frac_of_8TBps": achieved / 8000.0 if achieved else None,
         "other_kernels": {
-            "rowstats_kernel": {"ms": rows_ms, "algorithmic_GBps": 4.0 * E / (rows_ms * 1e-3) / 1e9 if rows_ms > 0 else None},
+            "rowstats_row_kernel": {"ms": rows_ms, "algorithmic_GBps": 4.0 * E / (rows_ms * 1e-3) / 1e9 if rows_ms > 0 else None},
             "lattice_kernel": {"ms": lat_ms, "bound": "latency"},
             "path_12B_per_elt_GBps": 12.0 * E / ((rows_ms + lat_ms + grad_ms) * 1e-3) / 1e9 if grad_ms > 0 else None,
         },

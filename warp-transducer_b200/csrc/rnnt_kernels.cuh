@@ -1,6 +1,7 @@
-// rnnt_kernels.cuh — the three sm_100a kernels of the RNN-T loss + gradient path.
+// rnnt_kernels.cuh — the three sm_100a kernels of the RNN-T loss + gradient path (each streaming
+// pass comes as a CTA-per-row kernel for long rows and a register-tile kernel for short rows).
 //
-//   rowstats_kernel  pass 1 over the logits [N,T,U,V]: per lattice cell the log-softmax statistics
+//   rowstats_*       pass 1 over the logits [N,T,U,V]: per lattice cell the log-softmax statistics
 //                    (row max m, log sum exp(x-m)) and the two log-probs the lattice needs
 //                    (blank, label y_u).      replaces reference reduce_max + reduce_exp
 //                    (include/detail/reduce.h:45-146, gpu_rnnt.h:73-80) and the per-step logp()
@@ -8,7 +9,7 @@
 //   lattice_kernel   alpha and beta anti-diagonal wavefronts, one CTA per (utterance, direction),
 //                    one thread per u, running concurrently.   replaces compute_alphas_kernel /
 //                    compute_betas_kernel (gpu_rnnt_kernel.h:11-47,79-113)
-//   grad_kernel      pass 2 over the logits: dense gradient w.r.t. logits, zeros on padded cells.
+//   grad_*           pass 2 over the logits: dense gradient w.r.t. logits, zeros on padded cells.
 //                    replaces cudaMemsetAsync + compute_grad_kernel (gpu_rnnt.h:107-110,
 //                    gpu_rnnt_kernel.h:143-179)
 //
@@ -399,7 +400,7 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
 // FADD (x-m), FFMA, MUFU.EX2 (+ FMUL when scale != 1).  The two special lanes (blank, label)
 // are patched per VECTOR, not per element.  Padded rows are written as zeros here (no memset pass).
 // =================================================================================================
-// Per-row constants of the gradient: offsets in the exp2 domain (see grad_kernel).
+// Per-row constants of the gradient: offsets in the exp2 domain (see the pass-2 header above).
 template <typename T> struct RowGrad {
     T m, cA, cB, cL;
     int y;
