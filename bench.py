@@ -247,22 +247,38 @@ def run_b200_arm(args):
     ul = torch.full((N,), L, dtype=torch.int32, device=dev)
     costs = torch.empty(N, device=dev)
     ws = torch.empty(wr.workspace_size(T, U, N, 4), dtype=torch.uint8, device=dev)
-    loss = torch.zeros(1, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The scalar-loss all-reduce runs on NCCL's own stream and is consumed one step later, so the
+    # compute stream of a rank never stalls on a slower peer inside a step (gradients are local;
+    # only the logged loss crosses ranks).  Two alternating buffers keep step k's reduction intact
+    # while step k+1 is enqueued.
+    loss2 = [torch.zeros(1, device=dev), torch.zeros(1, device=dev)]
+    state = {"k": 0, "pending": None}
+
     def step():
         wr.gpu_rnnt_async(acts, labels, tl, ul, costs, grads, 0, 1.0, ws)
-        torch.sum(costs, 0, keepdim=True, out=loss)
+        buf = loss2[state["k"] & 1]
+        torch.sum(costs, 0, keepdim=True, out=buf)
         if world > 1 and not os.environ.get("BENCH_NO_ALLREDUCE"):
-            dist.all_reduce(loss)      # the path's only exchange: one scalar over NVLink
+            if state["pending"] is not None:
+                state["pending"].wait()          # step k-1's collective: finished during this step's kernels
+            state["pending"] = dist.all_reduce(buf, async_op=True)   # one scalar over NVLink
+        state["k"] += 1
+
+    def drain():
+        if state["pending"] is not None:
+            state["pending"].wait()
+            state["pending"] = None
 
     wr.set_profiling(True)
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -273,6 +289,7 @@ def run_b200_arm(args):
         wr.profile_collect()                          # drop the warm-up records
         for _ in range(args.steps):
             step()                                    # no host synchronisation inside the timed region
+        drain()                                       # the last step's all-reduce is inside the timed region
         e1.record()
         barrier()
         total_ms = e0.elapsed_time(e1)
@@ -284,6 +301,7 @@ def run_b200_arm(args):
             flush.zero_()
             e0.record()
             step()
+            drain()
             e1.record()
             kms += np.array(wr.last_kernel_ms())
             e1.synchronize()
