@@ -276,17 +276,20 @@ def run_b200_arm(args):
             state["pending"] = None
 
     wr.set_profiling(True)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    drain()
-    barrier()
+    # everything with variable host cost (NVML init, thread start, event creation) happens BEFORE the
+    # barrier: ranks must leave it aligned, a late starter is waited for by all the others through
+    # the loss all-reduce and with K ~ 20 steps of 3.5 ms a 20 ms skew is a 30 % error
     sampler = ClockSampler(local)
     sampler.start()
     kms = np.zeros(3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    drain()
+    wr.profile_collect()                              # drop the warm-up records
+    barrier()
     if needs_no_flush(args.workload):
         e0.record()
-        wr.profile_collect()                          # drop the warm-up records
         for _ in range(args.steps):
             step()                                    # no host synchronisation inside the timed region
         drain()                                       # the last step's all-reduce is inside the timed region
@@ -362,9 +365,9 @@ def run_b200_arm(args):
         return tot
 
     e2e_steps = max(3, min(args.steps, 10))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_step()
     barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(e2e_steps):
         e2e_step()
