@@ -60,8 +60,10 @@ struct rnntOptions {
     int blank_label;          /* index of the blank symbol                                     */
     int maxT;                 /* time extent of the activation tensor                          */
     int maxU;                 /* label extent of the activation tensor (max label length + 1) */
-    bool batch_first;         /* ignored: the device path is always [N,T,U,V], as the
-                                 reference's GPU path is (include/detail/gpu_rnnt_kernel.h:7) */
+    bool batch_first;         /* ignored, as the reference's GPU path ignores it
+                                 (include/detail/gpu_rnnt_kernel.h:7 always indexes [N,T,U,V]; the
+                                 reference's tests/test_gpu.cu:42-50 leave it false with [N,T,U,V]
+                                 data).  For [T,U,N,V] tensors use rnnt_b200_loss_async_layout. */
 };
 #ifndef __cplusplus
 typedef struct rnntOptions rnntOptions;
@@ -181,6 +183,25 @@ rnntStatus_t rnnt_b200_backward_fp64(const double* const activations, double* gr
                                      double grad_scale, void* workspace, struct rnntOptions options);
 
 /*
+ * Explicit activation layout.  RNNT_B200_LAYOUT_TUNV takes activations and
+ * gradients as [maxT, maxU, minibatch, alphabet_size] - the layout the reference's CPU path indexes
+ * when batch_first == false (include/detail/cpu_rnnt.h:139-144) and that its GPU path never
+ * implemented.  Labels, lengths and costs stay [minibatch, ...].  Otherwise identical to
+ * compute_rnnt_loss_async (all pointers DEVICE, no synchronisation).
+ */
+enum { RNNT_B200_LAYOUT_NTUV = 0, RNNT_B200_LAYOUT_TUNV = 1 };
+rnntStatus_t rnnt_b200_loss_async_layout(int layout, const float* activations, float* gradients,
+                                         const int* flat_labels, const int* label_lengths,
+                                         const int* input_lengths, int alphabet_size, int minibatch,
+                                         float* costs_device, float grad_scale, void* workspace,
+                                         struct rnntOptions options);
+rnntStatus_t rnnt_b200_loss_async_layout_fp64(int layout, const double* activations, double* gradients,
+                                              const int* flat_labels, const int* label_lengths,
+                                              const int* input_lengths, int alphabet_size, int minibatch,
+                                              double* costs_device, double grad_scale, void* workspace,
+                                              struct rnntOptions options);
+
+/*
  * 16-bit storage variants: logits and gradients in bf16 or fp16, arithmetic,
  * lattice and costs in fp32; 6 B per logit instead of 12.  Same semantics as the async / split
  * entries above; workspace sized with dtype_size = sizeof(float).  dtype: RNNT_B200_BF16 / _FP16.
@@ -229,6 +250,12 @@ rnntStatus_t rnnt_b200_add_joint_backward(const float* trans, const float* pred,
                                           const int* label_lengths, const int* input_lengths,
                                           int alphabet_size, int minibatch, const float* grad_costs_device,
                                           float grad_scale, void* workspace, struct rnntOptions options);
+
+/* Debug / test hook: forward and backward log-likelihoods (natural log, as doubles on the host) that
+ * the last loss+gradient call left in `workspace`.  The reference checks their agreement in debug
+ * builds (include/detail/cpu_rnnt.h:167-170); tests/test_gpu_round2.py does the same.  Synchronises. */
+rnntStatus_t rnnt_b200_debug_log_likelihoods(const void* workspace, int maxT, int maxU, int minibatch,
+                                             size_t dtype_size, double* llf_host, double* llb_host);
 
 /* Number of kernels the last compute call on this thread launched (bench.py's gpu_launches). */
 int rnnt_b200_last_launch_count(void);

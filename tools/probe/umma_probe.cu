@@ -1,0 +1,77 @@
+// umma_probe.cu — checks warp-transducer_b200/csrc/rnnt_umma.cuh (tcgen05 tf32x3 GEMM) against a double
+// precision CPU product for the operand-layout combinations the additive-joint kernels use.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/probe/umma_probe tools/probe/umma_probe.cu
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../warp-transducer_b200/csrc/rnnt_umma.cuh"
+
+using namespace b200rnnt::umma;
+
+struct EpiStore {
+    float* out;   // [batch][slices][M][N]
+    int M, N, slices;
+    __device__ void operator()(int b, int slice, int m, int n, float v) const {
+        out[(((size_t)b * slices + slice) * M + m) * N + n] = v;
+    }
+};
+
+template <bool A_MN, bool B_MN, int NT, int KS>
+double run_case(const char* name, int batch, int M, int Nn, int K, int slices, int variant) {
+    // logical A[M][K], B[Nn][K]; stored K-major ([mn][k]) or MN-major ([k][mn])
+    std::vector<float> hA((size_t)batch * M * K), hB((size_t)batch * Nn * K);
+    srand(7);
+    for (auto& x : hA) x = (float)rand() / RAND_MAX;
+    for (auto& x : hB) x = (float)rand() / RAND_MAX;
+    float *dA, *dB, *dO;
+    cudaMalloc(&dA, hA.size() * 4);
+    cudaMalloc(&dB, hB.size() * 4);
+    const size_t no = (size_t)batch * slices * M * Nn;
+    cudaMalloc(&dO, no * 4);
+    cudaMemset(dO, 0xff, no * 4);
+    cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice);
+    Operand A{dA, (long long)M * K, A_MN ? 1 : K, A_MN ? M : 1, M};
+    Operand B{dB, (long long)Nn * K, B_MN ? 1 : K, B_MN ? Nn : 1, Nn};
+    auto kern = gemm_kernel<A_MN, B_MN, NT, KS, EpiStore>;
+    const size_t smem = gemm_smem_bytes<A_MN, B_MN, NT, KS>();
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(slices, (M + 127) / 128, batch);
+    kern<<<grid, 128, smem>>>(A, B, K, slices, EpiStore{dO, M, Nn, slices}, variant);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("%-28s variant %d: CUDA error %s\n", name, variant, cudaGetErrorString(e));
+        exit(1);
+    }
+    std::vector<float> hO(no);
+    cudaMemcpy(hO.data(), dO, no * 4, cudaMemcpyDeviceToHost);
+    double worst = 0;
+    for (int b = 0; b < batch; ++b)
+        for (int m = 0; m < M; ++m)
+            for (int n = 0; n < Nn; ++n) {
+                double ref = 0, got = 0;
+                for (int k = 0; k < K; ++k) {
+                    const double a = A_MN ? hA[((size_t)b * K + k) * M + m] : hA[((size_t)b * M + m) * K + k];
+                    const double bb = B_MN ? hB[((size_t)b * K + k) * Nn + n] : hB[((size_t)b * Nn + n) * K + k];
+                    ref += a * bb;
+                }
+                for (int s = 0; s < slices; ++s) got += hO[(((size_t)b * slices + s) * M + m) * Nn + n];
+                const double err = fabs(got - ref) / fmax(fabs(ref), 1e-30);
+                if (!(err <= worst)) worst = std::isnan(err) ? 1e30 : err;
+            }
+    printf("%-28s variant %d: batch %d M %d N %d K %d slices %d smem %zu B -> max rel err %.3e %s\n", name, variant, batch,
+           M, Nn, K, slices, smem, worst, worst < 1e-5 ? "OK" : "MISMATCH");
+    cudaFree(dA), cudaFree(dB), cudaFree(dO);
+    return worst;
+}
+
+int main() {
+    for (int variant = 0; variant < 4; ++variant) {
+        run_case<false, false, 32, 32>("S  (A K-major, B K-major)", 2, 150, 21, 1000, 3, variant);
+        run_case<true, false, 160, 24>("dF (A MN-major, B K-major)", 2, 200, 150, 21, 1, variant);
+        run_case<true, true, 32, 40>("dG (A MN-major, B MN-major)", 2, 200, 21, 150, 1, variant);
+    }
+    return 0;
+}

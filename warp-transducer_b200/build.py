@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libwarprnnt.so")
 SOURCES = ["rnnt_entry.cu"]
-DEPS = ["rnnt_entry.cu", "rnnt_kernels.cuh", "rnnt_common.cuh", os.path.join("..", "..", "include", "rnnt.h")]
+# every source/header under csrc/ plus the public header: editing any of them marks the .so stale
+DEPS = sorted(f for f in os.listdir(SRC) if f.endswith((".cu", ".cuh", ".h"))) + \
+       [os.path.join("..", "..", "include", "rnnt.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

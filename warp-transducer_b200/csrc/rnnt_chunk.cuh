@@ -1,0 +1,265 @@
+// rnnt_chunk.cuh — the two streaming passes for SHORT vocabulary rows (row <= 512 bytes: the README
+// small-vocabulary shape V=28 and the long-utterance shape V=50).
+//
+// A row of 28 or 50 floats is far too short to be a unit of work: per-row index decoding, length
+// checks, predicates on every vector slot and 8-byte loads (a 200-byte row is not 16-byte aligned)
+// made the register-tile kernels issue-bound at ~19 instructions per element (ncu, round 1:
+// smsp__issue_active 78 %, DRAM 75 %).  Here the unit is a CHUNK of R consecutive rows, which is
+// one contiguous, 16-byte aligned run of R*V elements in the activation tensor:
+//
+//   * ONE thread moves the whole chunk global -> shared memory with a 1-D TMA bulk copy
+//     (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP): no per-element load instructions, no
+//     alignment cases, the address generation is off the SM's issue slots.
+//   * While the copy is in flight every thread decodes its row and fetches the per-row scalars.
+//   * TPR threads share a row and walk it from shared memory element by element; TPR is the power
+//     of two dividing V (V=50 -> 2, V=28 -> 4), which makes the interleaved walk bank-conflict free
+//     (lane (i,h) touches word i*V + h + j*TPR: distinct banks across the warp).
+//   * Pass 2 overwrites the chunk in place with the gradient and ONE thread writes it back with a
+//     bulk shared -> global copy.
+//
+// Replaces (for short rows) reference reduce.h:10-146 + gpu_rnnt_kernel.h:5-9 (pass 1) and
+// gpu_rnnt.h:107-110 + gpu_rnnt_kernel.h:143-179 (pass 2).  Same outputs as the tile kernels in
+// rnnt_kernels.cuh: stat[row] = (max, log sum exp), lp2[skew] = (lp_blank, lp_label), dense gradient
+// with zeros on padded cells.  Short-lived CTAs on purpose (see rnnt_kernels.cuh).
+#pragma once
+#include "rnnt_kernels.cuh"
+
+namespace b200rnnt {
+
+// ---- mbarrier / bulk-copy PTX -------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Every waiting thread is SUSPENDED by the hardware for up to the hint (ns) per probe instead of
+// spinning: a CTA that waits for its chunk costs the SM no issue slots (pass 1 is issue-bound).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(2000u)
+            : "memory");
+    }
+}
+// global -> shared, completion counted in bytes on the mbarrier.  dst/src 16-B aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// shared -> global; the issuing thread waits until the source has been read before the CTA may exit
+__device__ __forceinline__ void bulk_s2g_and_wait(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T> struct ChunkThreads { static constexpr int value = sizeof(T) >= 8 ? 128 : 256; };
+
+// Stage rows [r0, r0+nrows) of the activation tensor into `tile`; returns after the data is visible
+// to every thread of the CTA.  Thread 0 has already decided that the chunk is worth reading.
+template <typename T>
+__device__ __forceinline__ void chunk_issue(const T* __restrict__ acts, T* tile, uint32_t bar, uint32_t r0,
+                                            uint32_t nrows, int V) {
+    // called by thread 0 only, before the CTA-wide barrier that publishes the mbarrier
+    const uint32_t bytes = nrows * (uint32_t)V * (uint32_t)sizeof(T);
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(tile), acts + (uint64_t)r0 * V, bytes, bar);
+}
+
+// =================================================================================================
+// Pass 1 on a chunk: per row (max, log sum exp) and the lattice's (blank, label) log-prob pair.
+// =================================================================================================
+template <typename T, int TPR>
+__global__ void __launch_bounds__(ChunkThreads<T>::value)
+rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels, const int* __restrict__ xlen,
+                      const int* __restrict__ ylen, typename Real<T>::pair* __restrict__ stat,
+                      typename Lat<T>::fac* __restrict__ lp2, const Dims d) {
+    using R = Real<T>;
+    constexpr int NT = ChunkThreads<T>::value;
+    constexpr int ROWS = NT / TPR;
+    extern __shared__ __align__(128) unsigned char chunk_raw[];
+    T* tile = reinterpret_cast<T*>(chunk_raw);
+    __shared__ __align__(8) unsigned long long bar_store;
+    const uint32_t bar = smem_u32(&bar_store);
+    const uint32_t r0 = blockIdx.x * ROWS;
+    const uint32_t nrows = min((uint32_t)ROWS, d.rows - r0);
+    const int V = d.V;
+    const bool bulk = ((nrows * (uint32_t)V * (uint32_t)sizeof(T)) & 15u) == 0;   // false only on a ragged last chunk
+    // the copy goes out first: thread 0 needs nothing but the chunk index for it
+    if (threadIdx.x == 0 && bulk) chunk_issue<T>(acts, tile, bar, r0, nrows, V);
+
+    // per-row bookkeeping while the copy is in flight
+    const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
+    const uint32_t r = r0 + i;
+    bool valid = (uint32_t)i < nrows;
+    uint32_t u = 0, b = 0, t = 0;
+    int Ub = 0, y = -1;
+    if (valid) {
+        int Tb;
+        d.decode(r, b, t, u);
+        utt_extent(d, xlen, ylen, b, Tb, Ub);
+        valid = (int)t < Tb && (int)u < Ub;
+        if (valid && h == 0 && (int)u < Ub - 1) y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+    }
+    // one barrier: publishes the mbarrier to the waiters and tells whether any row of the chunk is a
+    // real cell (a fully padded chunk - ragged batches only - costs one wasted read, nothing else)
+    const bool any_valid = __syncthreads_or(valid);
+    if (!any_valid) {
+        if (bulk && threadIdx.x == 0) mbar_wait(bar, 0);   // shared memory must outlive the in-flight copy
+        return;
+    }
+    if (bulk) {
+        mbar_wait(bar, 0);
+    } else {
+        const T* src = acts + (uint64_t)r0 * V;
+        for (uint32_t k = threadIdx.x; k < nrows * (uint32_t)V; k += NT) tile[k] = ld_scalar<T>(src + k);
+        __syncthreads();
+    }
+
+    const T* x = tile + (valid ? i : 0) * V;   // rows that are not valid walk row 0 (results discarded)
+    T m = R::neg_inf();
+#pragma unroll 4
+    for (int k = h; k < V; k += TPR) m = R::max(m, x[k]);
+    const T M = group_max<TPR>(m);
+    const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
+    T s = 0;
+#pragma unroll 4
+    for (int k = h; k < V; k += TPR) s += es.term(x[k]);
+    const T S = group_sum<TPR>(s);
+    if (valid && h == 0) {
+        const T lse = es.log_of(S);
+        typename R::pair st;
+        st.x = M;
+        st.y = lse;
+        stat[r] = st;
+        lp2[skew(d, b, t, u)] = Lat<T>::make((x[d.blank] - M) - lse, y >= 0 ? (x[y] - M) - lse : T(0), y >= 0);
+    }
+}
+
+// =================================================================================================
+// Pass 2 on a chunk: gradient in place in shared memory, one bulk store.  Formula and per-row
+// constants as grad_row_kernel (rnnt_kernels.cuh); the blank / label corrections are applied to the
+// two affected words of the row after the sweep.
+// =================================================================================================
+template <typename T, int TPR, bool SCALED>
+__global__ void __launch_bounds__(ChunkThreads<T>::value)
+grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
+                  const int* __restrict__ xlen, const int* __restrict__ ylen,
+                  const typename Real<T>::pair* __restrict__ stat, const typename Lat<T>::val* __restrict__ alphas,
+                  const typename Lat<T>::val* __restrict__ betas, const typename Lat<T>::val* __restrict__ llf, const T scale_in,
+                  const T* __restrict__ scale_vec, const Dims d) {
+    using R = Real<T>;
+    constexpr int NT = ChunkThreads<T>::value;
+    constexpr int ROWS = NT / TPR;
+    extern __shared__ __align__(128) unsigned char chunk_raw[];
+    T* tile = reinterpret_cast<T*>(chunk_raw);
+    __shared__ __align__(8) unsigned long long bar_store;
+    const uint32_t bar = smem_u32(&bar_store);
+    // chunks in reverse order: the tail of pass 1 is met first in L2
+    const uint32_t nchunks = gridDim.x;
+    const uint32_t r0 = (nchunks - 1 - blockIdx.x) * ROWS;
+    const uint32_t nrows = min((uint32_t)ROWS, d.rows - r0);
+    const int V = d.V;
+    const uint32_t nelem = nrows * (uint32_t)V;
+    const bool bulk = ((nelem * (uint32_t)sizeof(T)) & 15u) == 0;
+    if (threadIdx.x == 0 && bulk) chunk_issue<T>(acts, tile, bar, r0, nrows, V);   // the copy goes out first
+    T* gout = grads + (uint64_t)r0 * V;
+
+    const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
+    const bool inrange = (uint32_t)i < nrows;
+    const uint32_t r = r0 + (inrange ? i : 0);
+    bool valid;
+    RowGrad<T> rg;
+    T scale = scale_in;
+    {
+        uint32_t u, b, t;
+        int Tb, Ub;
+        d.decode(r, b, t, u);
+        if constexpr (sizeof(T) == 4) {
+            // every scalar of the row is requested in ONE round of loads, validity is sorted out afterwards
+            // (addresses are in bounds for any t, u of the tensor: see the workspace slack in carve())
+            rg = row_grad_setup_spec(d, r, b, t, u, xlen, ylen, labels, stat, alphas, betas, llf, Tb, Ub);
+            if (SCALED && scale_vec) scale = __ldg(scale_vec + b) * scale_in;
+            valid = inrange && (int)t < Tb && (int)u < Ub;
+        } else {
+            utt_extent(d, xlen, ylen, b, Tb, Ub);
+            valid = inrange && (int)t < Tb && (int)u < Ub;
+            rg.m = 0, rg.cA = 0, rg.cB = R::neg_inf(), rg.cL = R::neg_inf(), rg.y = -1;
+            if (valid) {
+                rg = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
+                if (SCALED && scale_vec) scale = __ldg(scale_vec + b) * scale_in;
+            }
+        }
+    }
+    // one barrier: publishes the mbarrier and tells whether any row of the chunk is a real cell
+    const bool any_valid = __syncthreads_or(valid);
+    if (!any_valid) {   // the whole chunk is padding: zeros straight to global memory
+        if (bulk) {
+            constexpr int VEC = 16 / sizeof(T);
+            VecT<T, VEC> z;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) z.v[c] = 0;
+            for (uint32_t k = threadIdx.x; k < nelem / VEC; k += NT) st_stream<T, VEC>(gout + (size_t)k * VEC, z);
+            if (threadIdx.x == 0) mbar_wait(bar, 0);   // shared memory must outlive the in-flight copy
+        } else {
+            for (uint32_t k = threadIdx.x; k < nelem; k += NT) gout[k] = T(0);
+        }
+        return;
+    }
+    if (bulk) {
+        mbar_wait(bar, 0);
+    } else {
+        const T* src = acts + (uint64_t)r0 * V;
+        for (uint32_t k = threadIdx.x; k < nelem; k += NT) tile[k] = ld_scalar<T>(src + k);
+        __syncthreads();
+    }
+
+    // Lanes sharing a row sit in one warp (TPR divides 32), so warp-level barriers order the reads of
+    // the two special logits, the in-place sweep and the corrections.
+    T* x = tile + (inrange ? i : 0) * V;
+    T xb = 0, xy = 0;
+    if (valid) {
+        xb = x[d.blank];
+        xy = x[rg.y >= 0 ? rg.y : 0];
+    }
+    __syncwarp();
+    if (valid) {
+#pragma unroll 4
+        for (int k = h; k < V; k += TPR) {
+            T g = R::exp2(fma(x[k] - rg.m, (T)R::kLog2e, rg.cA));
+            if (SCALED) g *= scale;
+            x[k] = g;
+        }
+    } else if (inrange) {
+        for (int k = h; k < V; k += TPR) x[k] = T(0);
+    }
+    __syncwarp();
+    if (valid && h == 0) {
+        T gb = R::exp2(fma(xb - rg.m, (T)R::kLog2e, rg.cB));
+        if (SCALED) gb *= scale;
+        x[d.blank] -= gb;
+        if (rg.y >= 0) {
+            T gl = R::exp2(fma(xy - rg.m, (T)R::kLog2e, rg.cL));
+            if (SCALED) gl *= scale;
+            x[rg.y] -= gl;
+        }
+    }
+    if (bulk) {
+        fence_async_smem();   // generic-proxy writes -> visible to the bulk copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) bulk_s2g_and_wait(gout, smem_u32(tile), nelem * (uint32_t)sizeof(T));
+    } else {
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < nelem; k += NT) gout[k] = tile[k];
+    }
+}
+
+}  // namespace b200rnnt

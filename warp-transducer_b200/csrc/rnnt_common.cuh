@@ -213,4 +213,74 @@ template <typename T> __device__ __forceinline__ double lse_step(double a, doubl
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 lattice storage (rnnt_lattice.cuh): values v * 2^e, transition factors m * 2^k.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEZero = -(1 << 29);        // exponent of "log zero"
+constexpr int kEDead = -(1 << 28);        // anything below this is reported as -inf
+constexpr float kMinLog2 = -65536.0f;     // transition log2-probabilities are clamped here (2^-65536 == 0)
+
+// log2 of a lattice value = e + l
+struct __align__(8) LogVal {
+    int e;
+    float l;
+};
+__device__ __forceinline__ float logval_log2(const LogVal a) { return (float)a.e + a.l; }
+
+// (m, k) with m * 2^k = e^lp, by round-to-nearest of lp*log2(e) with the 1.5*2^23 trick: FMA/ALU
+// pipes only.  NaN becomes m = NaN (the lattice kernel turns it into a NaN cost).
+__device__ __forceinline__ void split_prob(float lp, float& m, int& k) {
+    const float y = lp * 1.4426950408889634f;
+    const float yc = fmaxf(y, kMinLog2);
+    const float yk = yc + 12582912.0f;
+    k = __float_as_int(yk) - 0x4B400000;
+    const float f = yc - (yk - 12582912.0f);   // in [-0.5, 0.5]
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(f));
+    if (!(y > kMinLog2)) m = 1.0f, k = kEZero;   // probability zero (lp = -inf included)
+    if (lp != lp) m = lp;
+}
+// lattice factors of one cell: {m_blank, k_blank, m_label, k_label}; no label (u = U-1) -> log zero
+__device__ __forceinline__ float4 make_fac(float lp_blank, float lp_label, bool has_label) {
+    float mb, ml = 1.0f;
+    int kb, kl = kEZero;
+    split_prob(lp_blank, mb, kb);
+    if (has_label) split_prob(lp_label, ml, kl);
+    return make_float4(mb, __int_as_float(kb), ml, __int_as_float(kl));
+}
+// natural-log probabilities back from the factors (additive-joint weights kernel)
+__device__ __forceinline__ float fac_logp(float m, float kbits) {
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(m));
+    return ((float)__float_as_int(kbits) + l) * 0.6931471805599453f;
+}
+
+__device__ __forceinline__ LogVal to_logval(float v, int e) {
+    LogVal a;
+    a.e = e;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(a.l) : "f"(v));
+    return a;
+}
+
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Per-type lattice storage: what pass 1 writes per cell (`fac`) and what the wavefront stores (`val`).
+//   float : fac = {m_blank, k_blank, m_label, k_label} (16 B), val = LogVal {e, log2 v}
+//   double: fac = (lp_blank, lp_label) natural logs (16 B),    val = double natural log
+template <typename T> struct Lat;
+template <> struct Lat<float> {
+    using fac = float4;
+    using val = LogVal;
+    static __device__ __forceinline__ fac make(float lp_blank, float lp_label, bool has_label) {
+        return make_fac(lp_blank, lp_label, has_label);
+    }
+};
+template <> struct Lat<double> {
+    using fac = double2;
+    using val = double;
+    static __device__ __forceinline__ fac make(double lp_blank, double lp_label, bool has_label) {
+        return make_double2(lp_blank, has_label ? lp_label : 0.0);
+    }
+};
+
 }  // namespace b200rnnt

@@ -9,19 +9,23 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
 
 #include "../../include/rnnt.h"
+#include "rnnt_chunk.cuh"
 #include "rnnt_joint.cuh"
 #include "rnnt_kernels.cuh"
+#include "rnnt_lattice.cuh"
 
 using namespace b200rnnt;
 
 namespace {
 
 thread_local int g_last_launches = 0;
+thread_local bool g_layout_tunv = false;   // set only inside rnnt_b200_loss_async_layout*
 
 // Optional per-kernel timing (bench.py's roofline leg): when enabled, events are recorded on the
 // call's own stream around each of the three kernels, one event set per call (pooled), so a timed
@@ -92,11 +96,11 @@ SidePool& side_pool() {
 // ---- workspace carve-up (all sections 256-B aligned) -------------------------------------------
 struct Workspace {
     void* stat;     // pair<T>  [rows]   (row max, log sum exp)
-    void* lp2;      // pair<T>  [lat]    (blank, label) log-probs, diagonal-major
-    double* alphas; // [lat]   lat = N*(maxT+maxU-1)*maxU
-    double* betas;  // [lat]
-    double* llf;    // [N]
-    double* llb;    // [N]
+    void* lp2;      // Lat<T>::fac [lat]  per-cell transition factors (16 B), diagonal-major
+    void* alphas;   // Lat<T>::val [lat]  lat = N*(maxT+maxU-1)*maxU   (8 B: LogVal for fp32, double for fp64)
+    void* betas;    // Lat<T>::val [lat]
+    void* llf;      // Lat<T>::val [N]
+    void* llb;      // Lat<T>::val [N]
     void* costs;    // T [N]
     int* labels;    // staging for host-side integer inputs
     int* ylen;
@@ -114,16 +118,18 @@ Workspace carve(void* base, size_t rows, size_t lat, int N, int maxU, size_t dty
         return q;
     };
     w.stat = take(rows * 2 * dtype);
-    w.lp2 = take(lat * 2 * dtype);
-    w.alphas = static_cast<double*>(take(lat * sizeof(double)));
-    w.betas = static_cast<double*>(take(lat * sizeof(double)));
-    w.llf = static_cast<double*>(take(N * sizeof(double)));
-    w.llb = static_cast<double*>(take(N * sizeof(double)));
+    w.lp2 = take(lat * 16);
+    w.alphas = take(lat * 8);
+    w.betas = take(lat * 8);
+    w.llf = take((size_t)N * 8);
+    w.llb = take((size_t)N * 8);
     w.costs = take(N * dtype);
     w.labels = static_cast<int*>(take((size_t)N * (maxU > 1 ? maxU - 1 : 1) * sizeof(int)));
     w.ylen = static_cast<int*>(take(N * sizeof(int)));
     w.xlen = static_cast<int*>(take(N * sizeof(int)));
-    w.bytes = off + 256;  // slack for a base pointer that is not 256-aligned
+    // slack: a base pointer that is not 256-aligned, plus the speculative lattice reads one diagonal past
+    // the last utterance (row_grad_setup_spec: at most (maxU + 1) * 8 bytes beyond `betas`)
+    w.bytes = off + 256 + 16 * 1024;
     return w;
 }
 
@@ -160,7 +166,7 @@ void launch_rowstats_row(const IO* acts, const int* labels, const int* xlen, con
                          const Workspace& w, const Dims& d, cudaStream_t s) {
     rowstats_row_kernel<T, VEC, NV, IO><<<d.rows, RowThreads<IO>::value, 0, s>>>(
         acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
-        static_cast<typename Real<T>::pair*>(w.lp2), d);
+        static_cast<typename Lat<T>::fac*>(w.lp2), d);
     ++g_last_launches;
 }
 
@@ -170,8 +176,10 @@ void launch_grad_row(const IO* acts, IO* grads, const int* labels, const int* xl
     auto k = (scale != T(1) || scale_vec) ? grad_row_kernel<T, VEC, NV, true, IO>
                                           : grad_row_kernel<T, VEC, NV, false, IO>;
     k<<<d.rows, RowThreads<IO>::value, 0, s>>>(acts, grads, labels, xlen, ylen,
-                                      static_cast<const typename Real<T>::pair*>(w.stat), w.alphas,
-                                      w.betas, w.llf, scale, scale_vec, d);
+                                      static_cast<const typename Real<T>::pair*>(w.stat),
+                                      static_cast<const typename Lat<T>::val*>(w.alphas),
+                                      static_cast<const typename Lat<T>::val*>(w.betas),
+                                      static_cast<const typename Lat<T>::val*>(w.llf), scale, scale_vec, d);
     ++g_last_launches;
 }
 
@@ -181,7 +189,7 @@ void launch_rowstats_tile(const IO* acts, const int* labels, const int* xlen, co
     const uint64_t warps = ((uint64_t)d.rows * LPR + 31) / 32;
     rowstats_tile_kernel<T, VEC, LPR, IO><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(
         acts, labels, xlen, ylen, static_cast<typename Real<T>::pair*>(w.stat),
-        static_cast<typename Real<T>::pair*>(w.lp2), d);
+        static_cast<typename Lat<T>::fac*>(w.lp2), d);
     ++g_last_launches;
 }
 
@@ -193,7 +201,9 @@ void launch_grad_tile(const IO* acts, IO* grads, const int* labels, const int* x
     const uint64_t warps = ((uint64_t)d.rows * LPR + 31) / 32;
     k<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(acts, grads, labels, xlen, ylen,
                                                   static_cast<const typename Real<T>::pair*>(w.stat),
-                                                  w.alphas, w.betas, w.llf, scale, scale_vec, d);
+                                                  static_cast<const typename Lat<T>::val*>(w.alphas),
+                                                  static_cast<const typename Lat<T>::val*>(w.betas),
+                                                  static_cast<const typename Lat<T>::val*>(w.llf), scale, scale_vec, d);
     ++g_last_launches;
 }
 
@@ -254,9 +264,79 @@ void stream_passes(const IO* acts, IO* grads, const int* labels, const int* xlen
 #undef B200_TILE
 }
 
+// ---- short rows (<= 512 B): chunk kernels (rnnt_chunk.cuh), TMA bulk staging of R consecutive rows ----
+// threads per row = the power of two dividing V (bank-conflict-free interleaved walk), raised until a
+// thread owns at most 32 elements.  RNNT_B200_CHUNK=0 routes short rows to the register-tile kernels.
+inline int pick_tpr(int V) {
+    int tpr = 1;
+    while (tpr < 32 && V % (tpr * 2) == 0) tpr *= 2;
+    while (tpr < 32 && V > 32 * tpr) tpr *= 2;
+    return tpr;
+}
+inline bool chunk_enabled() {
+    static const bool on = [] { const char* e = getenv("RNNT_B200_CHUNK"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+template <typename T>
+bool chunk_pass(const T* acts, T* grads, const int* labels, const int* xlen, const int* ylen,
+                const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s, int pass) {
+    using Pair = typename Real<T>::pair;
+    using Fac = typename Lat<T>::fac;
+    using Val = typename Lat<T>::val;
+    if (!chunk_enabled() || (size_t)d.V * sizeof(T) > 512) return false;
+    if (reinterpret_cast<uintptr_t>(acts) % 16 || (pass == 2 && reinterpret_cast<uintptr_t>(grads) % 16)) return false;
+    constexpr int NT = ChunkThreads<T>::value;
+    const int tpr = pick_tpr(d.V);
+    const int rows_per = NT / tpr;
+    const unsigned grid = (unsigned)(((uint64_t)d.rows + rows_per - 1) / rows_per);
+    const size_t smem = (size_t)rows_per * d.V * sizeof(T);
+    const bool scaled = scale != T(1) || scale_vec;
+    // 8 chunk CTAs per SM need ~215 KB of shared memory: ask for the largest carve-out once per kernel
+    // (function attributes are per device: one bit per device ordinal)
+    auto prefer_smem = [](auto kernel) {
+        static thread_local unsigned long long done = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (!(done & bit)) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            done |= bit;
+        }
+        return kernel;
+    };
+#define B200_CHUNK(TPR)                                                                                     \
+    case TPR:                                                                                               \
+        if (pass == 1)                                                                                      \
+            prefer_smem(rowstats_chunk_kernel<T, TPR>)<<<grid, NT, smem, s>>>(acts, labels, xlen, ylen,                  \
+                                                                static_cast<Pair*>(w.stat), static_cast<Fac*>(w.lp2), d); \
+        else if (scaled)                                                                                    \
+            prefer_smem(grad_chunk_kernel<T, TPR, true>)<<<grid, NT, smem, s>>>(acts, grads, labels, xlen, ylen,         \
+                static_cast<const Pair*>(w.stat), static_cast<const Val*>(w.alphas),                        \
+                static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d);     \
+        else                                                                                                \
+            prefer_smem(grad_chunk_kernel<T, TPR, false>)<<<grid, NT, smem, s>>>(acts, grads, labels, xlen, ylen,        \
+                static_cast<const Pair*>(w.stat), static_cast<const Val*>(w.alphas),                        \
+                static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d);     \
+        break;
+    switch (tpr) {
+        B200_CHUNK(1)
+        B200_CHUNK(2)
+        B200_CHUNK(4)
+        B200_CHUNK(8)
+        B200_CHUNK(16)
+        B200_CHUNK(32)
+    }
+#undef B200_CHUNK
+    ++g_last_launches;
+    return true;
+}
+
 template <typename T, typename IO>
 void stream_pass(const IO* acts, IO* grads, const int* labels, const int* xlen, const int* ylen,
                  const Workspace& w, T scale, const T* scale_vec, const Dims& d, cudaStream_t s, int pass) {
+    if constexpr (std::is_same<T, IO>::value) {
+        if (chunk_pass<T>(acts, grads, labels, xlen, ylen, w, scale, scale_vec, d, s, pass)) return;
+    }
     // widest vector the row pitch and the base pointers allow (16-B vectors on the fast path)
     const uintptr_t mis = reinterpret_cast<uintptr_t>(acts) | reinterpret_cast<uintptr_t>(grads) |
                           ((uintptr_t)d.V * sizeof(IO));
@@ -311,6 +391,14 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
     d.rows = (uint32_t)rows64;
     d.divU = FastDiv(opt.maxU);
     d.divT = FastDiv(opt.maxT);
+    d.divN = FastDiv(N);
+    // options.batch_first is IGNORED on purpose, exactly as the reference's GPU path ignores it
+    // (include/detail/gpu_rnnt_kernel.h:7): the reference's own tests/test_gpu.cu:42-50 and
+    // tests/test_time.cu pass it zero-initialised (false) with [N,T,U,V] data, so honouring or
+    // rejecting it here would break every caller written against the reference.  The [T,U,N,V]
+    // layout the reference's CPU path indexes (include/detail/cpu_rnnt.h:139-144) is available through
+    // the explicit extension entry rnnt_b200_loss_async_layout (layout = RNNT_B200_LAYOUT_TUNV).
+    d.tmajor = g_layout_tunv ? 1 : 0;
 
     // Integer inputs: device pointers are used in place; host pointers (the header's literal
     // contract, reference include/rnnt.h:84-89) are staged through the workspace.
@@ -353,11 +441,11 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         Group g;
         g.w = w;
         g.w.stat = static_cast<Pair*>(w.stat) + (size_t)b0 * cell_stride;
-        g.w.lp2 = static_cast<Pair*>(w.lp2) + (size_t)b0 * lat_stride;
-        g.w.alphas = w.alphas + (size_t)b0 * lat_stride;
-        g.w.betas = w.betas + (size_t)b0 * lat_stride;
-        g.w.llf = w.llf + b0;
-        g.w.llb = w.llb + b0;
+        g.w.lp2 = static_cast<char*>(w.lp2) + (size_t)b0 * lat_stride * 16;
+        g.w.alphas = static_cast<char*>(w.alphas) + (size_t)b0 * lat_stride * 8;
+        g.w.betas = static_cast<char*>(w.betas) + (size_t)b0 * lat_stride * 8;
+        g.w.llf = static_cast<char*>(w.llf) + (size_t)b0 * 8;
+        g.w.llb = static_cast<char*>(w.llb) + (size_t)b0 * 8;
         g.d = d;
         g.d.N = nb;
         g.d.rows = (uint32_t)((size_t)nb * cell_stride);
@@ -374,17 +462,35 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
     auto launch_lattice = [&](const Group& g, cudaStream_t st) {
         const int threads = (opt.maxU + 31) / 32 * 32;
         dim3 grid(g.d.N, with_beta ? 2 : 1);
-        const size_t ring = (size_t)kRing * threads * sizeof(Pair);
-        auto launch = [&](auto kernel) {
-            // opt-in for rings above 48 KB (maxU > 768); set unconditionally when needed: the
-            // attribute is per device and the call is rare and cheap next to a >768-thread wavefront
-            if (ring > 48 * 1024)
-                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
-            kernel<<<grid, threads, ring, st>>>(static_cast<const Pair*>(g.w.lp2), g.xlen, g.ylen,
-                                               g.w.alphas, g.w.betas, g.w.llf, g.w.llb, g.costs, g.d);
-        };
-        if (threads > 32) launch(lattice_kernel<T, true>);
-        else launch(lattice_kernel<T, false>);
+        if constexpr (sizeof(T) == 4) {
+            // fp32: linear-domain wavefront with explicit exponents (rnnt_lattice.cuh)
+            const size_t ring = (size_t)kLinRing * threads * sizeof(float4);
+            auto launch = [&](auto kernel, int static_smem) {
+                if (ring + static_smem > 48 * 1024)
+                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+                kernel<<<grid, threads, ring, st>>>(static_cast<const float4*>(g.w.lp2), g.xlen, g.ylen,
+                                                   static_cast<LogVal*>(g.w.alphas), static_cast<LogVal*>(g.w.betas),
+                                                   static_cast<LogVal*>(g.w.llf), static_cast<LogVal*>(g.w.llb),
+                                                   g.costs, g.d);
+            };
+            if (threads > 32) launch(lattice_lin_kernel<true>, kLinStaticSmem);
+            else launch(lattice_lin_kernel<false>, 64);
+        } else {
+            // fp64: log-domain wavefront (rnnt_kernels.cuh)
+            const size_t ring = (size_t)kRing * threads * sizeof(double2);
+            auto launch = [&](auto kernel) {
+                // opt-in when static + dynamic shared memory exceed the 48 KB default (maxU >= 353);
+                // the attribute is per device and the call is rare and cheap next to such a wavefront
+                if (ring + kLatticeStaticSmem > 48 * 1024)
+                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+                kernel<<<grid, threads, ring, st>>>(static_cast<const double2*>(g.w.lp2), g.xlen, g.ylen,
+                                                   static_cast<double*>(g.w.alphas), static_cast<double*>(g.w.betas),
+                                                   static_cast<double*>(g.w.llf), static_cast<double*>(g.w.llb),
+                                                   g.costs, g.d);
+            };
+            if (threads > 32) launch(lattice_kernel<double, true>);
+            else launch(lattice_kernel<double, false>);
+        }
         ++g_last_launches;
     };
 
@@ -395,7 +501,7 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
     // lattice CTAs slow the streaming kernels a little, so the gain is modest, and there is none
     // when no pass 2 follows in the same call (loss-only / operator forward) - those stay in order.
     int groups = 1;
-    if (phase == kFull && grads && N >= 2 * kMaxGroups) {
+    if (phase == kFull && grads && N >= 2 * kMaxGroups && !d.tmajor) {
         static const int forced = [] { const char* e = getenv("RNNT_B200_GROUPS"); return e ? atoi(e) : 0; }();
         const double lattice_us = 0.25 * (opt.maxT + opt.maxU) + 20.0;
         const double stream_us = (double)rows64 * V * sizeof(IO) * (grads ? 3.0 : 1.0) / 6.9e6;
@@ -467,8 +573,8 @@ constexpr int kJointSlices = 16;  // max split-K slabs of the S = Ef.Eg^T contra
 inline int joint_slices(int V) { return std::max(1, std::min(kJointSlices, V / 320)); }
 struct JointWorkspace {
     float *ef, *eg, *mf, *mg, *inv_s, *wm, *bk, *lb, *part;
-    float2* lp2;
-    double *alphas, *betas, *llf, *llb;
+    float4* lp2;
+    LogVal *alphas, *betas, *llf, *llb;
     size_t bytes;
 };
 JointWorkspace carve_joint(void* base, int N, int T, int U, int V) {
@@ -490,11 +596,11 @@ JointWorkspace carve_joint(void* base, int N, int T, int U, int V) {
     w.bk = static_cast<float*>(take(C * 4));
     w.lb = static_cast<float*>(take(C * 4));
     w.part = static_cast<float*>(take(C * 4 * kJointSlices));
-    w.lp2 = static_cast<float2*>(take(D * 8));
-    w.alphas = static_cast<double*>(take(D * 8));
-    w.betas = static_cast<double*>(take(D * 8));
-    w.llf = static_cast<double*>(take((size_t)N * 8));
-    w.llb = static_cast<double*>(take((size_t)N * 8));
+    w.lp2 = static_cast<float4*>(take(D * 16));
+    w.alphas = static_cast<LogVal*>(take(D * 8));
+    w.betas = static_cast<LogVal*>(take(D * 8));
+    w.llf = static_cast<LogVal*>(take((size_t)N * 8));
+    w.llb = static_cast<LogVal*>(take((size_t)N * 8));
     w.bytes = off + 256;
     return w;
 }
@@ -525,6 +631,8 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     d.rows = (uint32_t)rows64;
     d.divU = FastDiv(U);
     d.divT = FastDiv(T);
+    d.divN = FastDiv(N);
+    d.tmajor = 0;
     const bool want_grad = dF != nullptr && phase != kForward;
     const bool with_beta = dF != nullptr || want_beta;
 
@@ -552,16 +660,14 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     {
         const int threads = (U + 31) / 32 * 32;
         dim3 grid(N, with_beta ? 2 : 1);
-        const size_t ring = (size_t)kRing * threads * sizeof(float2);
-        auto launch = [&](auto kernel) {
-            // opt-in for rings above 48 KB (maxU > 768); set unconditionally when needed: the
-            // attribute is per device and the call is rare and cheap next to a >768-thread wavefront
-            if (ring > 48 * 1024)
+        const size_t ring = (size_t)kLinRing * threads * sizeof(float4);
+        auto launch = [&](auto kernel, int static_smem) {
+            if (ring + static_smem > 48 * 1024)
                 cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
             kernel<<<grid, threads, ring, s>>>(w.lp2, xlen, ylen, w.alphas, w.betas, w.llf, w.llb, costs, d);
         };
-        if (threads > 32) launch(lattice_kernel<float, true>);
-        else launch(lattice_kernel<float, false>);
+        if (threads > 32) launch(lattice_lin_kernel<true>, kLinStaticSmem);
+        else launch(lattice_lin_kernel<false>, 64);
     }
     g_last_launches += 5;
     }  // phase != kBackward
@@ -689,6 +795,35 @@ rnntStatus_t rnnt_b200_backward_fp64(const double* const activations, double* gr
                        kBackward, false, workspace, options);
 }
 
+// ---- explicit activation layout ([N,T,U,V] or [T,U,N,V]) ------------------------------------------
+rnntStatus_t rnnt_b200_loss_async_layout(int layout, const float* activations, float* gradients,
+                                         const int* flat_labels, const int* label_lengths,
+                                         const int* input_lengths, int alphabet_size, int minibatch,
+                                         float* costs_device, float grad_scale, void* workspace,
+                                         rnntOptions options) {
+    if (layout != RNNT_B200_LAYOUT_NTUV && layout != RNNT_B200_LAYOUT_TUNV) return RNNT_STATUS_INVALID_VALUE;
+    g_layout_tunv = layout == RNNT_B200_LAYOUT_TUNV;
+    const rnntStatus_t st = run<float>(activations, gradients, flat_labels, label_lengths, input_lengths,
+                                       alphabet_size, minibatch, costs_device, true, grad_scale, nullptr, kFull,
+                                       false, workspace, options);
+    g_layout_tunv = false;
+    return st;
+}
+
+rnntStatus_t rnnt_b200_loss_async_layout_fp64(int layout, const double* activations, double* gradients,
+                                              const int* flat_labels, const int* label_lengths,
+                                              const int* input_lengths, int alphabet_size, int minibatch,
+                                              double* costs_device, double grad_scale, void* workspace,
+                                              rnntOptions options) {
+    if (layout != RNNT_B200_LAYOUT_NTUV && layout != RNNT_B200_LAYOUT_TUNV) return RNNT_STATUS_INVALID_VALUE;
+    g_layout_tunv = layout == RNNT_B200_LAYOUT_TUNV;
+    const rnntStatus_t st = run<double>(activations, gradients, flat_labels, label_lengths, input_lengths,
+                                        alphabet_size, minibatch, costs_device, true, grad_scale, nullptr, kFull,
+                                        false, workspace, options);
+    g_layout_tunv = false;
+    return st;
+}
+
 // ---- 16-bit storage (bf16 / fp16 logits and gradients, fp32 arithmetic and costs) ---------------
 rnntStatus_t rnnt_b200_loss_async_16(int dtype, const void* activations, void* gradients,
                                      const int* flat_labels, const int* label_lengths,
@@ -800,6 +935,36 @@ rnntStatus_t get_rnnt_workspace_size(int maxT, int maxU, int minibatch, bool gpu
 }
 
 int rnnt_b200_last_launch_count(void) { return g_last_launches; }
+
+// Debug / test hook: forward and backward log-likelihoods (natural log) left in a workspace by the last
+// call that produced both lattices.  The reference asserts their agreement in debug builds
+// (include/detail/cpu_rnnt.h:167-170).  Synchronises the device.
+rnntStatus_t rnnt_b200_debug_log_likelihoods(const void* workspace, int maxT, int maxU, int minibatch,
+                                             size_t dtype_size, double* llf_host, double* llb_host) {
+    if (!workspace || !llf_host || !llb_host || maxT <= 0 || maxU <= 0 || minibatch <= 0)
+        return RNNT_STATUS_INVALID_VALUE;
+    if (dtype_size != sizeof(double)) dtype_size = sizeof(float);
+    const size_t rows = (size_t)minibatch * maxT * maxU;
+    const size_t lat = (size_t)minibatch * (maxT + maxU - 1) * maxU;
+    const Workspace w = carve(const_cast<void*>(workspace), rows, lat, minibatch, maxU, dtype_size);
+    std::vector<unsigned char> f((size_t)minibatch * 8), b((size_t)minibatch * 8);
+    if (cudaDeviceSynchronize() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+    if (cudaMemcpy(f.data(), w.llf, f.size(), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(b.data(), w.llb, b.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return RNNT_STATUS_MEMOPS_FAILED;
+    for (int i = 0; i < minibatch; ++i) {
+        if (dtype_size == sizeof(double)) {
+            llf_host[i] = reinterpret_cast<const double*>(f.data())[i];
+            llb_host[i] = reinterpret_cast<const double*>(b.data())[i];
+        } else {
+            const LogVal lf = reinterpret_cast<const LogVal*>(f.data())[i];
+            const LogVal lb = reinterpret_cast<const LogVal*>(b.data())[i];
+            llf_host[i] = ((double)lf.e + (double)lf.l) * 0.6931471805599453;
+            llb_host[i] = ((double)lb.e + (double)lb.l) * 0.6931471805599453;
+        }
+    }
+    return RNNT_STATUS_SUCCESS;
+}
 
 void rnnt_b200_set_profiling(int enabled) { g_profile = enabled != 0; }
 

@@ -18,6 +18,7 @@
 // below; if max_k(f+g) is more than ~85 nats under mf+mg the fp32 sum underflows.
 #pragma once
 #include "rnnt_kernels.cuh"
+#include "rnnt_lattice.cuh"
 
 namespace b200rnnt {
 
@@ -122,7 +123,7 @@ struct EpiStats {
     const float *f, *g, *mf, *mg;
     const int *labels, *xlen, *ylen;
     float* inv_s;  // [N,T,U]
-    float2* lp2;   // diagonal-major lattice pairs
+    float4* lp2;   // diagonal-major lattice factors (Lat<float>::fac)
     JointDims jd;
     Dims d;        // lattice geometry (maxT = T, maxU = U)
     __device__ void operator()(int b, int t, int u, float S) const {
@@ -138,14 +139,14 @@ struct EpiStats {
         inv_s[cell] = 1.0f / S;
         const float* fr = f + ((size_t)b * jd.T + t) * jd.V;
         const float* gr = g + ((size_t)b * jd.U + u) * jd.V;
-        float2 lp;
-        lp.x = (__ldg(fr + jd.blank) + __ldg(gr + jd.blank)) - lse;
-        lp.y = 0.0f;
-        if (u < Ub - 1) {
+        const float lpb = (__ldg(fr + jd.blank) + __ldg(gr + jd.blank)) - lse;
+        float lpl = 0.0f;
+        const bool has_label = u < Ub - 1;
+        if (has_label) {
             const int y = __ldg(labels + (size_t)b * (jd.U > 1 ? jd.U - 1 : 0) + u);
-            lp.y = (__ldg(fr + y) + __ldg(gr + y)) - lse;
+            lpl = (__ldg(fr + y) + __ldg(gr + y)) - lse;
         }
-        lp2[skew(d, b, t, u)] = lp;
+        lp2[skew(d, b, t, u)] = make_fac(lpb, lpl, has_label);
     }
 };
 
@@ -164,8 +165,8 @@ joint_stats_kernel(const float* __restrict__ part, int slices, const EpiStats ep
 // ---- J3: per cell weights from the lattices ---------------------------------------------------------
 //   Wm = e^{alpha+beta-ll} / S ;  Bk = blank-transition occupancy ;  Lb = label-transition occupancy
 __global__ void __launch_bounds__(256)
-joint_weights_kernel(const float2* __restrict__ lp2, const double* __restrict__ alphas,
-                     const double* __restrict__ betas, const double* __restrict__ llf,
+joint_weights_kernel(const float4* __restrict__ lp2, const LogVal* __restrict__ alphas,
+                     const LogVal* __restrict__ betas, const LogVal* __restrict__ llf,
                      const float* __restrict__ inv_s, const int* __restrict__ xlen,
                      const int* __restrict__ ylen, float* __restrict__ Wm, float* __restrict__ Bk,
                      float* __restrict__ Lb, const float scale_in, const float* __restrict__ scale_vec,
@@ -181,12 +182,24 @@ joint_weights_kernel(const float2* __restrict__ lp2, const double* __restrict__ 
     const float scale = scale_vec ? scale_in * __ldg(scale_vec + b) : scale_in;
     if ((int)t < Tb && (int)u < Ub) {
         const size_t q = skew(d, b, t, u);
-        const float2 lp = lp2[q];
-        const double occ = alphas[q] - llf[b];
-        w = scale * expf((float)(occ + betas[q])) * inv_s[r];
-        if ((int)t < Tb - 1) bk = scale * expf((float)(occ + betas[q + d.maxU]) + lp.x);
-        else if ((int)u == Ub - 1) bk = scale * expf((float)occ + lp.x);
-        if ((int)u < Ub - 1) lb = scale * expf((float)(occ + betas[q + d.maxU + 1]) + lp.y);
+        // everything in the exp2 domain: log2 occupancy = exact integer part + small float part
+        const float4 fc = lp2[q];
+        const LogVal a = alphas[q], ll = llf[b], bq = betas[q];
+        const int oe = a.e - ll.e;
+        const float ol = a.l - ll.l;
+        const float lpb2 = (float)__float_as_int(fc.y) + log2f(fc.x);   // log2 p_blank
+        w = scale * exp2f((float)(oe + bq.e) + (ol + bq.l)) * inv_s[r];
+        if ((int)t < Tb - 1) {
+            const LogVal bn = betas[q + d.maxU];
+            bk = scale * exp2f((float)(oe + bn.e) + (ol + bn.l) + lpb2);
+        } else if ((int)u == Ub - 1) {
+            bk = scale * exp2f((float)oe + ol + lpb2);
+        }
+        if ((int)u < Ub - 1) {
+            const LogVal bn = betas[q + d.maxU + 1];
+            const float lpl2 = (float)__float_as_int(fc.w) + log2f(fc.z);
+            lb = scale * exp2f((float)(oe + bn.e) + (ol + bn.l) + lpl2);
+        }
     }
     Wm[r] = w;
     Bk[r] = bk;

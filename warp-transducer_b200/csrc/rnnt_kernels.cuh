@@ -22,7 +22,21 @@ namespace b200rnnt {
 struct Dims {
     int N, maxT, maxU, V, blank;
     uint32_t rows;  // N*maxT*maxU  (< 2^31)
-    FastDiv divU, divT;
+    FastDiv divU, divT, divN;
+    int tmajor;     // 0: activations [N,T,U,V] (batch_first);  1: [T,U,N,V] (rnntOptions.batch_first == false,
+                    // the layout reference include/detail/cpu_rnnt.h:139-144 indexes)
+    // physical row index (position of the V-vector in the activation tensor) -> lattice coordinates
+    __device__ __forceinline__ void decode(uint32_t r, uint32_t& b, uint32_t& t, uint32_t& u) const {
+        if (tmajor) {
+            uint32_t tu;
+            divN.divmod(r, tu, b);
+            divU.divmod(tu, t, u);
+        } else {
+            uint32_t bt;
+            divU.divmod(r, bt, u);
+            divT.divmod(bt, b, t);
+        }
+    }
 };
 
 // The lattice arrays (lp2, alphas, betas) are stored DIAGONAL-MAJOR per utterance: cell (t,u)
@@ -64,15 +78,14 @@ template <typename T, int VEC, int NV, typename IO = T>
 __global__ void __launch_bounds__(RowThreads<IO>::value, (sizeof(IO) >= 4 ? RNNT_ROWSTATS_MINB : 8))
 rowstats_row_kernel(const IO* __restrict__ acts, const int* __restrict__ labels,
                     const int* __restrict__ xlen, const int* __restrict__ ylen,
-                    typename Real<T>::pair* __restrict__ stat, typename Real<T>::pair* __restrict__ lp2,
+                    typename Real<T>::pair* __restrict__ stat, typename Lat<T>::fac* __restrict__ lp2,
                     const Dims d) {
     using R = Real<T>;
     constexpr int kRowThreads = RowThreads<IO>::value;
     __shared__ T sh_m[kRowThreads / 32], sh_s[kRowThreads / 32];
     const uint32_t r = blockIdx.x;
-    uint32_t bt, u, b, t;
-    d.divU.divmod(r, bt, u);
-    d.divT.divmod(bt, b, t);
+    uint32_t u, b, t;
+    d.decode(r, b, t, u);
     int Tb, Ub;
     utt_extent(d, xlen, ylen, b, Tb, Ub);
     if ((int)t >= Tb || (int)u >= Ub) return;  // padded cell: nothing to read (block-uniform)
@@ -127,14 +140,14 @@ rowstats_row_kernel(const IO* __restrict__ acts, const int* __restrict__ labels,
             st.x = M;
             st.y = lse;
             stat[r] = st;
-            typename R::pair lp;
-            lp.x = (ld_scalar<T>(row + d.blank) - M) - lse;
-            lp.y = 0;
-            if ((int)u < Ub - 1) {
+            const T lpb = (ld_scalar<T>(row + d.blank) - M) - lse;
+            T lpl = 0;
+            const bool has_label = (int)u < Ub - 1;
+            if (has_label) {
                 const int y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
-                lp.y = (ld_scalar<T>(row + y) - M) - lse;
+                lpl = (ld_scalar<T>(row + y) - M) - lse;
             }
-            lp2[skew(d, b, t, u)] = lp;
+            lp2[skew(d, b, t, u)] = Lat<T>::make(lpb, lpl, has_label);
         }
     }
 }
@@ -156,7 +169,7 @@ __global__ void __launch_bounds__(256)
 rowstats_tile_kernel(const IO* __restrict__ acts, const int* __restrict__ labels,
                      const int* __restrict__ xlen, const int* __restrict__ ylen,
                      typename Real<T>::pair* __restrict__ stat,
-                     typename Real<T>::pair* __restrict__ lp2, const Dims d) {
+                     typename Lat<T>::fac* __restrict__ lp2, const Dims d) {
     using R = Real<T>;
     constexpr int RPW = kWarp / LPR;
     const int lane = threadIdx.x & 31;
@@ -168,11 +181,10 @@ rowstats_tile_kernel(const IO* __restrict__ acts, const int* __restrict__ labels
         const uint64_t r0 = gw * RPW;
         const uint32_t r = (uint32_t)r0 + sub;
         bool valid = r0 + sub < d.rows;
-        uint32_t bt = 0, u = 0, b = 0, t = 0;
+        uint32_t u = 0, b = 0, t = 0;
         int Tb = 0, Ub = 0;
         if (valid) {
-            d.divU.divmod(r, bt, u);
-            d.divT.divmod(bt, b, t);
+            d.decode(r, b, t, u);
             utt_extent(d, xlen, ylen, b, Tb, Ub);
             valid = (int)t < Tb && (int)u < Ub;
         }
@@ -207,14 +219,14 @@ rowstats_tile_kernel(const IO* __restrict__ acts, const int* __restrict__ labels
             st.x = M;
             st.y = lse;
             stat[r] = st;
-            typename R::pair lp;
-            lp.x = (ld_scalar<T>(row + d.blank) - M) - lse;
-            lp.y = 0;
-            if ((int)u < Ub - 1) {
+            const T lpb = (ld_scalar<T>(row + d.blank) - M) - lse;
+            T lpl = 0;
+            const bool has_label = (int)u < Ub - 1;
+            if (has_label) {
                 const int y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
-                lp.y = (ld_scalar<T>(row + y) - M) - lse;
+                lpl = (ld_scalar<T>(row + y) - M) - lse;
             }
-            lp2[skew(d, b, t, u)] = lp;
+            lp2[skew(d, b, t, u)] = Lat<T>::make(lpb, lpl, has_label);
         }
     }
 }
@@ -237,6 +249,7 @@ rowstats_tile_kernel(const IO* __restrict__ acts, const int* __restrict__ labels
 //    SHFL -> DADD -> DADD -> F2F -> FMNMX/FMUL -> MUFU.EX2 -> FADD -> MUFU.LG2 -> FMUL -> F2F -> DADD.
 // =================================================================================================
 constexpr int kRing = 8;
+constexpr int kLatticeStaticSmem = 2 * 32 * (int)sizeof(double);   // lattice_kernel's `edge` exchange slots
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
@@ -252,14 +265,17 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 template <typename T> __device__ __forceinline__ double lse2(double x, double y) {
     if (sizeof(T) == 4) {
         const float df = (float)(x - y);          // +-inf when one side is -inf, NaN when both are
+        // (-inf) - (-inf) is the only legitimate NaN here; a NaN operand (a NaN logit upstream)
+        // must reach the cost, as the reference's log_plus lets it (rnnt_helper.h:16-24)
+        if (!(df == df)) return (x == y) ? x : x + y;
         const double mx = df > 0.0f ? x : y;
-        // min(.,0) turns the NaN of (-inf)-(-inf) into 0: the result is then y + ln2 = -inf
-        const float nd = fminf(-fabsf(df), 0.0f) * 1.4426950408889634f;
+        const float nd = -fabsf(df) * 1.4426950408889634f;
         float e, l;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(nd));
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
         return mx + (double)(l * 0.6931471805599453f);
     } else {
+        if (x != x || y != y) return x + y;   // fmax/fmin drop a NaN operand; the reference's log_plus keeps it
         const double mx = fmax(x, y), mn = fmin(x, y);
         if (mx == -(double)INFINITY) return mx;
         return mx + log1p(::exp(mn - mx));
@@ -432,35 +448,103 @@ __device__ __forceinline__ VecT<T, VEC> grad_vec(const VecT<T, VEC>& x, const Ro
     }
     return g;
 }
-template <typename T>
-__device__ __forceinline__ RowGrad<T> row_grad_setup(const Dims& d, uint32_t r, uint32_t b, uint32_t t,
-                                                     uint32_t u, int Tb, int Ub,
-                                                     const int* __restrict__ labels,
-                                                     const typename Real<T>::pair* __restrict__ stat,
-                                                     const double* __restrict__ alphas,
-                                                     const double* __restrict__ betas,
-                                                     const double* __restrict__ llf) {
-    using R = Real<T>;
-    RowGrad<T> g;
-    const typename R::pair st = __ldg(stat + r);
+// fp64: lattices are natural-log doubles
+__device__ __forceinline__ RowGrad<double> row_grad_setup(const Dims& d, uint32_t r, uint32_t b, uint32_t t,
+                                                          uint32_t u, int Tb, int Ub,
+                                                          const int* __restrict__ labels,
+                                                          const double2* __restrict__ stat,
+                                                          const double* __restrict__ alphas,
+                                                          const double* __restrict__ betas,
+                                                          const double* __restrict__ llf) {
+    using R = Real<double>;
+    RowGrad<double> g;
+    const double2 st = __ldg(stat + r);
     const size_t q = skew(d, b, t, u);  // (t+1,u) is at q + maxU, (t,u+1) at q + maxU + 1
     const double occ = alphas[q] - __ldg(llf + b);
     g.m = st.x;
-    g.cA = ((T)(occ + betas[q]) - st.y) * (T)R::kLog2e;
+    g.cA = ((occ + betas[q]) - st.y) * R::kLog2e;
     g.cB = R::neg_inf();
     g.cL = R::neg_inf();
     if ((int)t < Tb - 1)
-        g.cB = ((T)(occ + betas[q + d.maxU]) - st.y) * R::kLog2e;
+        g.cB = ((occ + betas[q + d.maxU]) - st.y) * R::kLog2e;
     else if ((int)u == Ub - 1)
-        g.cB = ((T)occ - st.y) * R::kLog2e;
+        g.cB = (occ - st.y) * R::kLog2e;
     g.y = -1;
     if ((int)u < Ub - 1) {
-        g.cL = ((T)(occ + betas[q + d.maxU + 1]) - st.y) * R::kLog2e;
+        g.cL = ((occ + betas[q + d.maxU + 1]) - st.y) * R::kLog2e;
         g.y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
     }
     return g;
 }
-
+// fp32: lattices are LogVal {e, log2 v}: the offsets are formed in the exp2 domain from an exact integer
+// part and a small float part - no conversions to double, no FP64 pipe
+__device__ __forceinline__ RowGrad<float> row_grad_setup(const Dims& d, uint32_t r, uint32_t b, uint32_t t,
+                                                         uint32_t u, int Tb, int Ub,
+                                                         const int* __restrict__ labels,
+                                                         const float2* __restrict__ stat,
+                                                         const LogVal* __restrict__ alphas,
+                                                         const LogVal* __restrict__ betas,
+                                                         const LogVal* __restrict__ llf) {
+    using R = Real<float>;
+    RowGrad<float> g;
+    const float2 st = __ldg(stat + r);
+    const size_t q = skew(d, b, t, u);
+    const LogVal a = alphas[q], ll = llf[b], bq = betas[q];
+    const int oe = a.e - ll.e;            // occupancy exponent alpha - ll (exact)
+    const float ol = a.l - ll.l - st.y * R::kLog2e;
+    g.m = st.x;
+    g.cA = (float)(oe + bq.e) + (ol + bq.l);
+    g.cB = R::neg_inf();
+    g.cL = R::neg_inf();
+    if ((int)t < Tb - 1) {
+        const LogVal bn = betas[q + d.maxU];
+        g.cB = (float)(oe + bn.e) + (ol + bn.l);
+    } else if ((int)u == Ub - 1) {
+        g.cB = (float)oe + ol;
+    }
+    g.y = -1;
+    if ((int)u < Ub - 1) {
+        const LogVal bn = betas[q + d.maxU + 1];
+        g.cL = (float)(oe + bn.e) + (ol + bn.l);
+        g.y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+    }
+    return g;
+}
+// Same constants with every load issued unconditionally and at once (short rows: the row's scalars are
+// the critical path of a chunk CTA, two dependent rounds of loads cost ~1 us).  Reads are in bounds for
+// every (t,u) of the tensor: q + maxU + 1 stays inside the lattice arrays plus the slack carve() leaves.
+__device__ __forceinline__ RowGrad<float> row_grad_setup_spec(const Dims& d, uint32_t r, uint32_t b, uint32_t t,
+                                                              uint32_t u, const int* __restrict__ xlen,
+                                                              const int* __restrict__ ylen,
+                                                              const int* __restrict__ labels,
+                                                              const float2* __restrict__ stat,
+                                                              const LogVal* __restrict__ alphas,
+                                                              const LogVal* __restrict__ betas,
+                                                              const LogVal* __restrict__ llf, int& Tb, int& Ub) {
+    using R = Real<float>;
+    const size_t q = skew(d, b, t, u);
+    const int xl = __ldg(xlen + b), yl = __ldg(ylen + b);
+    const float2 st = __ldg(stat + r);
+    const LogVal a = alphas[q], ll = llf[b], bq = betas[q], bt = betas[q + d.maxU], bu = betas[q + d.maxU + 1];
+    const int lab = (int)u < d.maxU - 1 ? __ldg(labels + (size_t)b * (d.maxU - 1) + u) : 0;
+    Tb = min(max(xl, 1), d.maxT);
+    Ub = min(max(yl + 1, 1), d.maxU);
+    RowGrad<float> g;
+    const int oe = a.e - ll.e;
+    const float ol = a.l - ll.l - st.y * R::kLog2e;
+    g.m = st.x;
+    g.cA = (float)(oe + bq.e) + (ol + bq.l);
+    g.cB = R::neg_inf();
+    if ((int)t < Tb - 1) g.cB = (float)(oe + bt.e) + (ol + bt.l);
+    else if ((int)u == Ub - 1) g.cB = (float)oe + ol;
+    g.cL = R::neg_inf();
+    g.y = -1;
+    if ((int)u < Ub - 1) {
+        g.cL = (float)(oe + bu.e) + (ol + bu.l);
+        g.y = lab;
+    }
+    return g;
+}
 
 // Pass 2, long rows: one CTA per row, non-persistent (same reasoning as rowstats_row_kernel).  All
 // of a thread's loads are issued before the row's lattice constants are fetched, so both latencies
@@ -472,15 +556,14 @@ template <typename T, int VEC, int NV, bool SCALED, typename IO = T>
 __global__ void __launch_bounds__(RowThreads<IO>::value, (sizeof(IO) >= 4 ? RNNT_GRAD_MINB : 6))
 grad_row_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int* __restrict__ labels,
                 const int* __restrict__ xlen, const int* __restrict__ ylen,
-                const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
-                const double* __restrict__ betas, const double* __restrict__ llf, const T scale_in,
+                const typename Real<T>::pair* __restrict__ stat, const typename Lat<T>::val* __restrict__ alphas,
+                const typename Lat<T>::val* __restrict__ betas, const typename Lat<T>::val* __restrict__ llf, const T scale_in,
                 const T* __restrict__ scale_vec,
                 const Dims d) {
     constexpr int kRowThreads = RowThreads<IO>::value;
     const uint32_t r = d.rows - 1 - blockIdx.x;
-    uint32_t bt, u, b, t;
-    d.divU.divmod(r, bt, u);
-    d.divT.divmod(bt, b, t);
+    uint32_t u, b, t;
+    d.decode(r, b, t, u);
     int Tb, Ub;
     utt_extent(d, xlen, ylen, b, Tb, Ub);
     const int nv = d.V / VEC;
@@ -505,7 +588,7 @@ grad_row_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int* 
         }
     };
     load(threadIdx.x);  // in flight before the lattice constants are fetched
-    const RowGrad<T> rg = row_grad_setup<T>(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
+    const RowGrad<T> rg = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
     auto emit = [&](int base) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
@@ -527,8 +610,8 @@ template <typename T, int VEC, int LPR, bool SCALED, typename IO = T>
 __global__ void __launch_bounds__(256)
 grad_tile_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int* __restrict__ labels,
                  const int* __restrict__ xlen, const int* __restrict__ ylen,
-                 const typename Real<T>::pair* __restrict__ stat, const double* __restrict__ alphas,
-                 const double* __restrict__ betas, const double* __restrict__ llf, const T scale_in,
+                 const typename Real<T>::pair* __restrict__ stat, const typename Lat<T>::val* __restrict__ alphas,
+                 const typename Lat<T>::val* __restrict__ betas, const typename Lat<T>::val* __restrict__ llf, const T scale_in,
                 const T* __restrict__ scale_vec,
                  const Dims d) {
     constexpr int RPW = kWarp / LPR;
@@ -542,9 +625,8 @@ grad_tile_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int*
         const uint64_t rr = gw * RPW + sub;
         if (rr >= d.rows) continue;
         const uint32_t r = d.rows - 1 - (uint32_t)rr;
-        uint32_t bt, u, b, t;
-        d.divU.divmod(r, bt, u);
-        d.divT.divmod(bt, b, t);
+        uint32_t u, b, t;
+        d.decode(r, b, t, u);
         int Tb, Ub;
         utt_extent(d, xlen, ylen, b, Tb, Ub);
         const IO* row = acts + (uint64_t)r * d.V;
@@ -567,7 +649,7 @@ grad_tile_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int*
             const int i = sl + j * LPR;
             if (i < nv) x[j] = ld_stream<T, VEC>(row + (size_t)i * VEC);
         }
-        const RowGrad<T> rg = row_grad_setup<T>(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
+        const RowGrad<T> rg = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
 #pragma unroll
         for (int j = 0; j < kVPL; ++j) {
             const int i = sl + j * LPR;

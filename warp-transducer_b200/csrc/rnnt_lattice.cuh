@@ -1,0 +1,266 @@
+// rnnt_lattice.cuh — fp32 alpha/beta wavefronts in the LINEAR domain with an explicit exponent.
+//
+// The log-domain recurrence (lattice_kernel in rnnt_kernels.cuh, kept for fp64) puts
+// SHFL -> DADD -> DADD -> F2F -> FMUL -> MUFU.EX2 -> FADD -> MUFU.LG2 -> FMUL -> F2F -> DADD on the
+// dependent chain of every anti-diagonal: ~390 cycles per step on sm_100 (round 1: 200-240 ns per
+// diagonal whatever the batch).  Here a lattice value is  v * 2^e  with v a float in [1,2) and e an
+// int, and a transition probability is  m * 2^k  (m in [0.71,1.42], k int), both prepared by pass 1:
+//
+//   product   v*m, e+k                                         FMUL || IADD          (4 cycles)
+//   sum       E = max(e1,e2);  v = v1*2^(e1-E) + v2*2^(e2-E)   VIMNMX, IADD, VIMNMX, IMAD, FMUL/FFMA
+//   renorm    e = E + exponent(v) - 127;  v = mantissa(v)      SHF, IADD3 || LOP3
+//
+// no MUFU, no conversions and no FP64 on the chain (~60 cycles + the shuffle).  "log zero" is
+// (1, kEZero): alignment shifts are clamped to 2^-120, so such a term can never contribute and no
+// -inf special cases are needed.  Values are stored as LogVal {e, log2 v} (8 B, the same size as the
+// double the fp64 path stores); the gradient kernels consume them in the exp2 domain directly.
+//
+// Warps of one utterance are DECOUPLED: each thread fetches only its own column's factors (cp.async
+// ring, completion counted per thread), the u-1 / u+1 neighbour inside a warp comes by shuffle, and
+// across warps through a small tagged ring in shared memory (producer lane publishes {v,e,tag}, the
+// consumer lane prefetches one step ahead and spins only if the tag is not there yet).  A downstream
+// warp therefore settles a step or two behind its upstream neighbour and the shared-memory round trip
+// leaves the dependent chain; there is no __syncthreads in the step loop.
+//
+// Replaces reference compute_alphas_kernel / compute_betas_kernel (gpu_rnnt_kernel.h:11-47,79-113)
+// and log_sum_exp (rnnt_helper.h:16-24) for fp32.
+#pragma once
+#include "rnnt_kernels.cuh"
+
+namespace b200rnnt {
+
+// v1*2^e1 + v2*2^e2, normalised
+__device__ __forceinline__ void lin_add(float v1, int e1, float v2, int e2, float& v, int& e) {
+    const int E = max(e1, e2);
+    const int d1 = min(E - e1, 120), d2 = min(E - e2, 120);
+    const float s1 = __int_as_float(0x3f800000 - (d1 << 23));
+    const float s2 = __int_as_float(0x3f800000 - (d2 << 23));
+    const float w = fmaf(v2, s2, v1 * s1);
+    const int bits = __float_as_int(w);
+    e = max(E + (bits >> 23) - 127, kEZero);
+    v = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+}
+constexpr int kLinRing = 8;    // diagonals of factors in flight per thread (the step loop is unrolled by this)
+constexpr int kEdge = 16;      // slots of the cross-warp exchange ring (multiple of kLinRing, power of two)
+constexpr int kEdgeWarps = 32;
+constexpr int kLinStaticSmem = kEdgeWarps * kEdge * 16 + kEdgeWarps * 4 + 16;
+
+// ---- shared memory by 32-bit shared-space address (no generic->shared conversion in the step loop) ----
+__device__ __forceinline__ void cp_async16_s(uint32_t dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// ---- cross-warp exchange.  One 16-byte slot = {v bits, tag, e, tag}: each 8-byte half carries the tag,
+// so a torn slot shows mismatching tags.  The producer's ONE publishing lane stores (predicated, no
+// branch); the consumer warp reads the slot with ALL lanes (same address: a broadcast), so the "is it
+// there yet" test and the spin are warp-uniform and the shuffles around them stay convergent. ----------
+__device__ __forceinline__ void edge_publish(uint32_t slot, float v, int e, int tag, bool pred) {
+    asm volatile(
+        "{ .reg .pred p; setp.ne.b32 p, %5, 0; @p st.volatile.shared.v4.b32 [%0], {%1, %2, %3, %2}; }" ::"r"(slot),
+        "r"(__float_as_int(v)), "r"(tag), "r"(e), "r"(0), "r"((int)pred)
+        : "memory");
+}
+__device__ __forceinline__ bool edge_read(uint32_t slot, int tag, float& v, int& e) {
+    int a, b, c, d;
+    asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(slot) : "memory");
+    v = __int_as_float(a);
+    e = c;
+    return b == tag && d == tag;
+}
+__device__ __forceinline__ int lds_volatile(uint32_t addr) {
+    int v;
+    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile(uint32_t addr, int v) {
+    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// =================================================================================================
+// grid = (N, 1 or 2): blockIdx.y 0 -> alpha, 1 -> beta.  One thread per u, blockDim = maxU rounded up
+// to a warp.  Step s = 0..last visits anti-diagonal n = s (alpha) or n = last - s (beta); thread u
+// owns cell (n - u, u).
+// =================================================================================================
+template <bool MULTI, bool BACKWARD>
+__device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac, const int* __restrict__ xlen,
+                                                 const int* __restrict__ ylen, LogVal* __restrict__ out,
+                                                 LogVal* __restrict__ llout, float* __restrict__ costs,
+                                                 const Dims& d, uint32_t ring_base, uint32_t edge_base,
+                                                 uint32_t prog_base, int* bad_any) {
+    constexpr int DIR = BACKWARD ? -1 : 1;
+    const int b = blockIdx.x;
+    const int u = threadIdx.x;
+    const int NT = blockDim.x;
+    const int lane = u & 31;
+    // broadcast from lane 0 so the compiler treats the warp index (and everything derived from it:
+    // has_src / has_dst, the exchange addresses) as warp-uniform - no divergence handling in the step loop
+    const int warp = __shfl_sync(0xffffffffu, u >> 5, 0);
+    int Tb, Ub;
+    utt_extent(d, xlen, ylen, b, Tb, Ub);
+    const size_t base = (size_t)b * lattice_block(d);
+    const int last = Tb + Ub - 2;
+    const int mU = d.maxU;
+    const int nactive = (Ub + 31) >> 5;   // warps that own at least one column
+    if (MULTI && warp >= nactive) return;  // no column of this warp exists in this utterance
+
+    const unsigned width = u < Ub ? (unsigned)Tb : 0u;   // thread u is active on diagonals n with n - u < width
+    const uint32_t step_bytes = NT * 16;
+    uint32_t ring_u = ring_base + u * 16;                // this thread's column of the ring
+    asm volatile("" : "+r"(ring_u));                     // opaque: keep it in a register, do not rematerialise the cvta
+    const int dstep = DIR * mU;                          // pointer step per diagonal in step order
+    const int n0 = BACKWARD ? last : 0;
+    const float4* gp = fac + base + u + (ptrdiff_t)n0 * mU;  // next diagonal to fetch
+    LogVal* sp = out + base + u + (ptrdiff_t)n0 * mU;
+    int nu = n0 - u;                                     // (current diagonal) - u: active iff (unsigned)nu < width
+#pragma unroll
+    for (int k = 0; k < kLinRing - 1; ++k) {
+        if ((unsigned)(nu + k * DIR) < width) cp_async16_s(ring_u + k * step_bytes, gp);
+        cp_async_commit();
+        gp += dstep;
+    }
+    // running value.  alpha: (sv,se) = alpha(t,u) p_blank(t,u) offered to (t+1,u), (ov,oe) = alpha(t,u)
+    // p_label(t,u) offered to (t,u+1).  beta: (sv,se) = beta(t+1,u).
+    float sv = 1.0f, ov = 1.0f;
+    int se = kEZero, oe = kEZero;
+    if (!BACKWARD && u == 0) se = 0;                     // alpha(0,0) = 1 enters as the "stay" term of step 0
+    if (BACKWARD && u == Ub - 1) se = 0;                 // virtual beta(T, U-1) = 1
+    float nansum = 0.0f;                                 // NaN factor anywhere -> NaN here
+    // cross-warp neighbour (warp-uniform): alpha reads warp-1's lane 31, beta reads warp+1's lane 0
+    const bool has_src = MULTI && (BACKWARD ? warp + 1 < nactive : warp > 0);
+    const bool has_dst = MULTI && (BACKWARD ? warp > 0 : warp + 1 < nactive);
+    const bool edge_lane = BACKWARD ? lane == 31 : lane == 0;   // the lane without a neighbour inside the warp
+    const bool pub_lane = BACKWARD ? lane == 0 : lane == 31;    // the lane whose value the next warp needs
+    const uint32_t src_edge = edge_base + (BACKWARD ? warp + 1 : warp - 1) * (kEdge * 16);
+    const uint32_t my_edge = edge_base + warp * (kEdge * 16);
+    const uint32_t dst_prog = prog_base + (BACKWARD ? warp - 1 : warp + 1) * 4;
+    float pv = 1.0f;   // cross-warp value for the coming step (prefetched)
+    int pe = kEZero;
+    bool pok = true;
+
+    for (int s0 = 0; s0 <= last; s0 += kLinRing) {
+        const uint32_t eoff = (uint32_t)(s0 & (kEdge - 1)) * 16;
+        if (MULTI && has_dst) {
+            // do not lap the consumer: this pass writes slots that hold the steps of one pass ago
+            while (lds_volatile(dst_prog) < s0 - kLinRing) {}
+        }
+#pragma unroll
+        for (int j = 0; j < kLinRing; ++j) {
+            const int s = s0 + j;
+            if (s > last) break;
+            cp_async_wait<kLinRing - 2>();   // this thread's factors of the current diagonal have landed
+            // refill the slot of the previous step (private to this thread, already consumed)
+            if ((unsigned)(nu + (kLinRing - 1) * DIR) < width)
+                cp_async16_s(ring_u + ((j + kLinRing - 1) % kLinRing) * step_bytes, gp);
+            cp_async_commit();
+            gp += dstep;
+            const bool active = (unsigned)nu < width;
+            float4 f = make_float4(1.0f, 0.0f, 1.0f, 0.0f);
+            if (active) f = lds128(ring_u + j * step_bytes);
+
+            // neighbour's value from the previous step
+            float nv;
+            int ne;
+            if (BACKWARD) {
+                nv = __shfl_down_sync(0xffffffffu, sv, 1);
+                ne = __shfl_down_sync(0xffffffffu, se, 1);
+            } else {
+                nv = __shfl_up_sync(0xffffffffu, ov, 1);
+                ne = __shfl_up_sync(0xffffffffu, oe, 1);
+            }
+            if (MULTI && has_src) {
+                // value of step s-1 (tag s) from the neighbouring warp; at s == 0 nothing beside is active
+                const uint32_t slot = src_edge + ((eoff + (uint32_t)(j + kEdge - 1) * 16) & (kEdge * 16 - 1));
+                if (s > 0)
+                    while (!pok) pok = __all_sync(0xffffffffu, edge_read(slot, s, pv, pe));
+                if (edge_lane) nv = pv, ne = pe;
+            } else if (edge_lane) {
+                nv = 1.0f, ne = kEZero;
+            }
+            if (active) {
+                nansum += f.x + f.z;
+                const int kb = __float_as_int(f.y), kl = __float_as_int(f.w);
+                float v;
+                int e;
+                if (BACKWARD) {
+                    // beta(t,u) = beta(t+1,u) p_blank(t,u) + beta(t,u+1) p_label(t,u)
+                    lin_add(sv * f.x, se + kb, nv * f.z, ne + kl, v, e);
+                    sv = v, se = e;
+                } else {
+                    // alpha(t,u) = [alpha(t-1,u) p_blank(t-1,u)] + [alpha(t,u-1) p_label(t,u-1)]
+                    lin_add(sv, se, nv, ne, v, e);
+                    sv = v * f.x, se = e + kb;   // offered to (t+1, u)
+                    ov = v * f.z, oe = e + kl;   // offered to (t, u+1)
+                }
+                *sp = to_logval(v, e);
+            }
+            sp += dstep;
+            nu += DIR;
+            if (MULTI) {
+                const uint32_t slot_off = (eoff + (uint32_t)j * 16) & (kEdge * 16 - 1);
+                if (has_dst) edge_publish(my_edge + slot_off, BACKWARD ? sv : ov, BACKWARD ? se : oe, s + 1, pub_lane);
+                if (has_src) {
+                    sts_volatile(prog_base + warp * 4, s);   // every lane, same value: progress of this warp
+                    pok = __all_sync(0xffffffffu, edge_read(src_edge + slot_off, s + 1, pv, pe));   // prefetch for the next step
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // NaN anywhere in this utterance's factors -> NaN cost (the reference propagates it through log_plus)
+    bool bad = nansum != nansum;
+    if (MULTI) {
+        if (bad) atomicOr(bad_any, 1);
+        asm volatile("bar.sync 1, %0;" ::"r"(nactive * 32) : "memory");
+        bad = *(volatile int*)bad_any != 0;
+    } else {
+        bad = __any_sync(0xffffffffu, bad);
+    }
+    if (!BACKWARD) {
+        if (u == Ub - 1) {
+            // sv, se = alpha(T-1,U-1) p_blank(T-1,U-1) after the last step
+            LogVal ll = to_logval(sv, se);
+            float cost = -(logval_log2(ll) * 0.6931471805599453f);
+            if (se < kEDead) cost = INFINITY;
+            if (bad) {
+                cost = __int_as_float(0x7fc00000);
+                ll.l = cost;
+            }
+            llout[b] = ll;
+            costs[b] = cost;
+        }
+    } else if (u == 0) {
+        LogVal ll = to_logval(sv, se);
+        if (bad) ll.l = __int_as_float(0x7fc00000);
+        llout[b] = ll;
+    }
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(1024)
+lattice_lin_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen, const int* __restrict__ ylen,
+                   LogVal* __restrict__ alphas, LogVal* __restrict__ betas, LogVal* __restrict__ llf,
+                   LogVal* __restrict__ llb, float* __restrict__ costs, const Dims d) {
+    extern __shared__ __align__(16) unsigned char ring_raw[];   // [kLinRing][blockDim.x] float4, thread-private columns
+    __shared__ __align__(16) int4 edge[MULTI ? kEdgeWarps * kEdge : 1];
+    __shared__ int prog[MULTI ? kEdgeWarps : 1];
+    __shared__ int bad_any;
+    if (MULTI) {
+        // tags start at 0 (= nothing published), progress at -1
+        for (int i = threadIdx.x; i < kEdgeWarps * kEdge; i += blockDim.x) edge[i] = make_int4(0, 0, 0, 0);
+        if (threadIdx.x < kEdgeWarps) prog[threadIdx.x] = -1;
+        if (threadIdx.x == 0) bad_any = 0;
+        __syncthreads();
+    }
+    const uint32_t ring_base = smem_u32(ring_raw), edge_base = smem_u32(edge), prog_base = smem_u32(prog);
+    if (blockIdx.y == 0)
+        lattice_lin_body<MULTI, false>(fac, xlen, ylen, alphas, llf, costs, d, ring_base, edge_base, prog_base, &bad_any);
+    else
+        lattice_lin_body<MULTI, true>(fac, xlen, ylen, betas, llb, costs, d, ring_base, edge_base, prog_base, &bad_any);
+}
+
+}  // namespace b200rnnt

@@ -36,6 +36,7 @@ class _RNNT(Function):
         if not acts.is_cuda:
             raise RuntimeError("warprnnt_pytorch (B200 build) runs on CUDA tensors only; "
                                "there is no CPU fallback")
+        warp_rnnt.require_same_device(acts, labels=labels, act_lens=act_lens, label_lens=label_lens)
         if reduction not in ('none', 'sum', 'mean'):
             raise ValueError("reduction must be 'none', 'sum' or 'mean'")
         minibatch_size = acts.size(0)

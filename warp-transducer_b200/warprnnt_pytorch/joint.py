@@ -69,7 +69,7 @@ def add_joint_call(trans, pred, labels, act_lens, label_lens, costs, dtrans, dpr
         opt = warp_rnnt.rnntOptions(loc=1, num_threads=0,
                                     stream=torch.cuda.current_stream(trans.device).cuda_stream,
                                     blank_label=blank, maxT=T, maxU=U, batch_first=True)
-        lab = labels.data_ptr() if labels.numel() else labels.new_zeros(1).data_ptr()
+        lab = warp_rnnt._labels_ptr(labels)
         st = _lib.rnnt_b200_add_joint_loss(trans.data_ptr(), pred.data_ptr(),
                                            dtrans.data_ptr() if dtrans is not None else None,
                                            dpred.data_ptr() if dpred is not None else None,
@@ -86,8 +86,7 @@ def _joint_opts(trans, pred, blank):
                                  blank_label=blank, maxT=trans.shape[1], maxU=pred.shape[1], batch_first=True)
 
 
-def _lab_ptr(labels):
-    return labels.data_ptr() if labels.numel() else labels.new_zeros(1).data_ptr()
+_lab_ptr = warp_rnnt._labels_ptr   # cached per-device stand-in when there are no labels (U == 1)
 
 
 class _AddJointRNNT(Function):
@@ -99,6 +98,7 @@ class _AddJointRNNT(Function):
         certify_joint_inputs(trans, pred, labels, act_lens, label_lens)
         if not trans.is_cuda:
             raise RuntimeError("warprnnt_pytorch (B200 build) runs on CUDA tensors only")
+        warp_rnnt.require_same_device(trans, pred=pred, labels=labels, act_lens=act_lens, label_lens=label_lens)
         if reduction not in ('none', 'sum', 'mean'):
             raise ValueError("reduction must be 'none', 'sum' or 'mean'")
         N, T, V = trans.shape

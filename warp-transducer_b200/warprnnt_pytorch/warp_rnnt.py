@@ -57,6 +57,11 @@ _lib.rnnt_b200_forward_16.argtypes = [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int,
 _lib.rnnt_b200_backward_16.restype = C.c_int
 _lib.rnnt_b200_backward_16.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P, rnntOptions]
 RNNT_B200_BF16, RNNT_B200_FP16 = 1, 2
+_lib.rnnt_b200_loss_async_layout.restype = C.c_int
+_lib.rnnt_b200_loss_async_layout.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_float, _P, rnntOptions]
+_lib.rnnt_b200_loss_async_layout_fp64.restype = C.c_int
+_lib.rnnt_b200_loss_async_layout_fp64.argtypes = [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_double, _P, rnntOptions]
+RNNT_B200_LAYOUT_NTUV, RNNT_B200_LAYOUT_TUNV = 0, 1
 _lib.get_workspace_size.restype = C.c_int
 _lib.get_workspace_size.argtypes = [C.c_int, C.c_int, C.c_int, C.c_bool, C.POINTER(C.c_size_t), C.c_size_t]
 _lib.get_warprnnt_version.restype = C.c_int
@@ -124,9 +129,27 @@ def _ptr(t):
     return t.data_ptr() if t is not None and t.numel() > 0 else None
 
 
+_DUMMY_LABELS = {}   # device -> 1-element int32 tensor, kept alive for the life of the process
+
+
 def _labels_ptr(labels):
-    # U == 1 (no labels at all): the ABI still wants a non-null pointer
-    return labels.data_ptr() if labels.numel() > 0 else labels.new_zeros(1).data_ptr()
+    """U == 1 (no labels at all): the ABI still wants a non-null pointer.  The stand-in is a cached
+    per-device tensor - a temporary would be freed before the (asynchronous) launch reads it."""
+    if labels.numel() > 0:
+        return labels.data_ptr()
+    key = (labels.device.type, labels.device.index)
+    if key not in _DUMMY_LABELS:
+        _DUMMY_LABELS[key] = torch.zeros(1, dtype=torch.int32, device=labels.device)
+    return _DUMMY_LABELS[key].data_ptr()
+
+
+def require_same_device(ref, **tensors):
+    """The async entry points dereference every pointer on `ref`'s device (host staging exists only in
+    the synchronous C API), so a CPU or other-GPU tensor would be an illegal access, not an error."""
+    for name, t in tensors.items():
+        if t is not None and t.device != ref.device:
+            raise RuntimeError("%s is on %s but the activations are on %s: all operator inputs must "
+                               "live on the activations' CUDA device" % (name, t.device, ref.device))
 
 
 def gpu_rnnt(acts, labels, input_lengths, label_lengths, costs, grads, blank_label, num_threads):
@@ -176,6 +199,27 @@ def gpu_rnnt_async(acts, labels, input_lengths, label_lengths, costs, grads, bla
         st = _lib.rnnt_b200_loss_async_16(code, *args) if code else fn(*args)
     if st != RNNT_STATUS_SUCCESS:
         raise RuntimeError("compute_rnnt_loss_async failed: " + status_string(st))
+    return workspace
+
+
+def gpu_rnnt_async_tunv(acts, labels, input_lengths, label_lengths, costs, grads, blank_label,
+                        grad_scale=1.0, workspace=None):
+    """Time-major extension: `acts` / `grads` are [T, U, N, V] (the layout the reference's CPU path
+    indexes for batch_first == false, cpu_rnnt.h:139-144); labels [N, U-1], lengths and costs [N].
+    fp32 / fp64, no host synchronisation.  Returns the workspace tensor."""
+    T, U, N, V = acts.shape
+    fn, esz = _pick(acts, "rnnt_b200_loss_async_layout", "rnnt_b200_loss_async_layout_fp64")
+    with torch.cuda.device(acts.device):
+        need = workspace_size(T, U, N, esz)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=acts.device)
+        opt = _options(acts, blank_label)
+        opt.maxT, opt.maxU = T, U
+        st = fn(RNNT_B200_LAYOUT_TUNV, acts.data_ptr(), _ptr(grads), _labels_ptr(labels),
+                label_lengths.data_ptr(), input_lengths.data_ptr(), V, N, costs.data_ptr(), grad_scale,
+                workspace.data_ptr(), opt)
+    if st != RNNT_STATUS_SUCCESS:
+        raise RuntimeError("rnnt_b200_loss_async_layout failed: " + status_string(st))
     return workspace
 
 
@@ -231,6 +275,21 @@ def gpu_rnnt_backward(acts, labels, input_lengths, label_lengths, grads, grad_co
     if st != RNNT_STATUS_SUCCESS:
         raise RuntimeError("rnnt_b200_backward failed: " + status_string(st))
     return 0
+
+
+_lib.rnnt_b200_debug_log_likelihoods.restype = C.c_int
+_lib.rnnt_b200_debug_log_likelihoods.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_size_t, _P, _P]
+
+
+def read_log_likelihoods(workspace, maxT, maxU, minibatch, dtype_size=4):
+    """(llForward, llBackward) of the last loss+gradient call that used `workspace` (test hook)."""
+    import numpy as np
+    f, b = np.zeros(minibatch), np.zeros(minibatch)
+    st = _lib.rnnt_b200_debug_log_likelihoods(workspace.data_ptr(), maxT, maxU, minibatch, dtype_size,
+                                              f.ctypes.data, b.ctypes.data)
+    if st != RNNT_STATUS_SUCCESS:
+        raise RuntimeError("rnnt_b200_debug_log_likelihoods: " + status_string(st))
+    return f, b
 
 
 def profile_collect():
