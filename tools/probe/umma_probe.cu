@@ -10,16 +10,8 @@
 
 using namespace b200rnnt::umma;
 
-struct EpiStore {
-    float* out;   // [batch][slices][M][N]
-    int M, N, slices;
-    __device__ void operator()(int b, int slice, int m, int n, float v) const {
-        out[(((size_t)b * slices + slice) * M + m) * N + n] = v;
-    }
-};
-
-template <bool A_MN, bool B_MN, int NT, int KS>
-double run_case(const char* name, int batch, int M, int Nn, int K, int slices, int variant) {
+template <bool A_MN, bool B_MN, int NT, int KS, int AMODE = (A_MN ? 0 : 1), int BMODE = (B_MN ? 0 : 1)>
+double run_case(const char* name, int batch, int M, int Nn, int K, int slices) {
     // logical A[M][K], B[Nn][K]; stored K-major ([mn][k]) or MN-major ([k][mn])
     std::vector<float> hA((size_t)batch * M * K), hB((size_t)batch * Nn * K);
     srand(7);
@@ -35,14 +27,14 @@ double run_case(const char* name, int batch, int M, int Nn, int K, int slices, i
     cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice);
     Operand A{dA, (long long)M * K, A_MN ? 1 : K, A_MN ? M : 1, M};
     Operand B{dB, (long long)Nn * K, B_MN ? 1 : K, B_MN ? Nn : 1, Nn};
-    auto kern = gemm_kernel<A_MN, B_MN, NT, KS, EpiStore>;
-    const size_t smem = gemm_smem_bytes<A_MN, B_MN, NT, KS>();
+    auto kern = gemm_kernel<AMODE, BMODE, NT, KS>;
+    const size_t smem = gemm_smem_bytes<NT, KS>();
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid(slices, (M + 127) / 128, batch);
-    kern<<<grid, 128, smem>>>(A, B, K, slices, EpiStore{dO, M, Nn, slices}, variant);
+    dim3 grid(slices * ((Nn + NT - 1) / NT), (M + 127) / 128, batch);
+    kern<<<grid, kThreads, smem>>>(A, B, K, slices, Epilogue{nullptr, 0, 0, 0, dO, (long long)M * Nn, (long long)slices * M * Nn, Nn, 1});
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        printf("%-28s variant %d: CUDA error %s\n", name, variant, cudaGetErrorString(e));
+        printf("%-28s: CUDA error %s\n", name, cudaGetErrorString(e));
         exit(1);
     }
     std::vector<float> hO(no);
@@ -61,17 +53,23 @@ double run_case(const char* name, int batch, int M, int Nn, int K, int slices, i
                 const double err = fabs(got - ref) / fmax(fabs(ref), 1e-30);
                 if (!(err <= worst)) worst = std::isnan(err) ? 1e30 : err;
             }
-    printf("%-28s variant %d: batch %d M %d N %d K %d slices %d smem %zu B -> max rel err %.3e %s\n", name, variant, batch,
+    printf("%-28s: batch %d M %d N %d K %d slices %d smem %zu B -> max rel err %.3e %s\n", name, batch,
            M, Nn, K, slices, smem, worst, worst < 1e-5 ? "OK" : "MISMATCH");
     cudaFree(dA), cudaFree(dB), cudaFree(dO);
     return worst;
 }
 
 int main() {
-    for (int variant = 0; variant < 4; ++variant) {
-        run_case<false, false, 32, 32>("S  (A K-major, B K-major)", 2, 150, 21, 1000, 3, variant);
-        run_case<true, false, 160, 24>("dF (A MN-major, B K-major)", 2, 200, 150, 21, 1, variant);
-        run_case<true, true, 32, 40>("dG (A MN-major, B MN-major)", 2, 200, 21, 150, 1, variant);
-    }
+    run_case<false, false, 32, 24>("S  (A k-contig scalar, B k-contig scalar)", 2, 150, 21, 1000, 3);
+    run_case<true, false, 160, 24>("dF (A mn-contig, B k-contig)", 2, 200, 150, 21, 1);
+    run_case<true, true, 32, 24>("dG (A mn-contig, B mn-contig)", 2, 200, 21, 150, 1);
+    run_case<false, false, 32, 32, 2, 2>("S  full size, float4 fetch", 4, 150, 21, 5000, 8);
+    run_case<false, false, 64, 32, 2, 2>("S  N=64, float4 fetch", 2, 70, 66, 1000, 3);
+    run_case<true, true, 64, 24>("dG N=64", 2, 200, 66, 70, 1);
+    run_case<true, false, 64, 24>("dF N=64 tiled", 2, 200, 150, 21, 1);
+    run_case<false, false, 32, 32, 2, 2>("S  one stage", 2, 150, 21, 24, 1);
+    run_case<false, false, 32, 32, 2, 2>("S  two stages", 2, 150, 21, 60, 1);
+    run_case<true, false, 192, 24>("dF N=192", 2, 200, 150, 21, 1);
+    run_case<true, false, 256, 24>("dF N=256 tiled", 1, 200, 300, 40, 1);
     return 0;
 }

@@ -1,5 +1,5 @@
 set -x
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -30
-echo "== default groups"; timeout 300 python tools/quick_time.py c2 c3 c4
-echo "== GROUPS=1"; RNNT_B200_GROUPS=1 timeout 300 python tools/quick_time.py c4
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r2a.json 2> gpurun_out/bench_r2a.err; echo "bench rc=$?"; tail -5 gpurun_out/bench_r2a.err; cat gpurun_out/bench_r2a.json | head -c 6000
+timeout 120 ./tools/probe/umma_probe
+timeout 600 python -m pytest tests/test_gpu_add_joint.py -q 2>&1 | tail -4
+timeout 300 python tools/joint_time.py
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_joint_r2.csv python tools/joint_profile_target.py > /dev/null 2>&1

@@ -63,6 +63,20 @@ inline int read_set(EventSet& es, float* ms3) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncSetAttribute once per (kernel, attribute, device) and host thread.  Keyed by the kernel's
+// address: template instantiations with identical signatures share a function-pointer TYPE, so a static
+// flag inside a generic lambda would be shared between them.
+void func_attr_once(const void* kernel, cudaFuncAttribute attr, int value) {
+    struct Key { const void* k; int attr, dev; };
+    thread_local std::vector<Key> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const Key& e : done)
+        if (e.k == kernel && e.attr == (int)attr && e.dev == dev) return;
+    cudaFuncSetAttribute(kernel, attr, value);
+    done.push_back(Key{kernel, (int)attr, dev});
+}
+
 // Side streams for overlapping the (latency-bound, few-SM) lattice kernel of one group of
 // utterances with the (bandwidth-bound) streaming passes of the others.  High priority so the
 // lattice CTAs are placed as soon as short-lived streaming CTAs retire.  Fork/join with events on
@@ -294,14 +308,8 @@ bool chunk_pass(const T* acts, T* grads, const int* labels, const int* xlen, con
     // 8 chunk CTAs per SM need ~215 KB of shared memory: ask for the largest carve-out once per kernel
     // (function attributes are per device: one bit per device ordinal)
     auto prefer_smem = [](auto kernel) {
-        static thread_local unsigned long long done = 0;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const unsigned long long bit = 1ull << (dev & 63);
-        if (!(done & bit)) {
-            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            done |= bit;
-        }
+        func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
         return kernel;
     };
 #define B200_CHUNK(TPR)                                                                                     \
@@ -605,6 +613,27 @@ JointWorkspace carve_joint(void* base, int N, int T, int U, int V) {
     return w;
 }
 
+// ---- tensor-core contractions of the additive joint (rnnt_umma.cuh) ---------------------------------
+// N (accumulator columns per CTA) is the smallest instantiated width that holds `n`, tiled beyond 256.
+inline bool joint_umma_enabled() {
+    static const bool on = [] { const char* e = getenv("RNNT_B200_JOINT_SIMT"); return !(e && atoi(e) != 0); }();
+    return on;
+}
+template <int A_MODE, int B_MODE, int KS>
+void launch_umma(const umma::Operand& A, const umma::Operand& B, int m, int n, int K, int slices, int batch,
+                 const umma::Epilogue& epi, cudaStream_t s, int max_tile = 256) {
+    auto go = [&](auto kernel, int NT, size_t smem) {
+        func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid((unsigned)(slices * ((n + NT - 1) / NT)), (unsigned)((m + 127) / 128), (unsigned)batch);
+        kernel<<<grid, umma::kThreads, smem, s>>>(A, B, K, slices, epi);
+    };
+    if (n <= 32) go(umma::gemm_kernel<A_MODE, B_MODE, 32, KS>, 32, umma::gemm_smem_bytes<32, KS>());
+    else if (n <= 64 || max_tile <= 64) go(umma::gemm_kernel<A_MODE, B_MODE, 64, KS>, 64, umma::gemm_smem_bytes<64, KS>());
+    else if (n <= 128) go(umma::gemm_kernel<A_MODE, B_MODE, 128, KS>, 128, umma::gemm_smem_bytes<128, KS>());
+    else if (n <= 192) go(umma::gemm_kernel<A_MODE, B_MODE, 192, KS>, 192, umma::gemm_smem_bytes<192, KS>());
+    else go(umma::gemm_kernel<A_MODE, B_MODE, 256, KS>, 256, umma::gemm_smem_bytes<256, KS>());
+}
+
 rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG, const int* labels,
                            const int* ylen, const int* xlen, int V, int N, float* costs, float scale,
                            const float* scale_vec, Phase phase, bool want_beta, void* workspace,
@@ -642,16 +671,28 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     joint_prep_kernel<<<(N * U + 7) / 8, 256, 0, s>>>(g, w.eg, w.mg, N * U, V);
     // J2: S = Ef . Eg^T in kJointSlices deterministic K-slabs, then lse + lattice log-prob pairs
     {
-        Operand A{w.ef, (size_t)T * V, V, 1}, B{w.eg, (size_t)U * V, V, 1};
         const int slices = joint_slices(V);
-        dim3 grid((U + 63) / 64, (T + 63) / 64, N * slices);
-        if (U <= 32) {
-            grid.x = (U + 31) / 32;
-            joint_gemm_kernel<EpiPartial, 32, 32><<<grid, 256, 0, s>>>(
-                A, B, T, U, V, slices, EpiPartial{w.part, (size_t)rows64, T, U, slices});
+        if (joint_umma_enabled()) {
+            // tcgen05: M = t (tiles of 128), N = u, K = v split into `slices` slabs
+            umma::Operand A{w.ef, (long long)T * V, V, 1, T}, B{w.eg, (long long)U * V, V, 1, U};
+            // float4 operand fetches when every row of Ef / Eg starts on a 16-byte boundary
+            // partial sums of slice ks land in slab ks: part[ks][b][t][u]
+            const umma::Epilogue epi{nullptr, 0, 0, 0, w.part, (long long)rows64, (long long)T * U, U, 1};
+            if (V % 4 == 0)
+                launch_umma<2, 2, 32>(A, B, T, U, V, slices, N, epi, s);
+            else
+                launch_umma<1, 1, 32>(A, B, T, U, V, slices, N, epi, s);
         } else {
-            joint_gemm_kernel<EpiPartial, 64, 32><<<grid, 256, 0, s>>>(
-                A, B, T, U, V, slices, EpiPartial{w.part, (size_t)rows64, T, U, slices});
+            Operand A{w.ef, (size_t)T * V, V, 1}, B{w.eg, (size_t)U * V, V, 1};
+            dim3 grid((U + 63) / 64, (T + 63) / 64, N * slices);
+            if (U <= 32) {
+                grid.x = (U + 31) / 32;
+                joint_gemm_kernel<EpiPartial, 32, 32><<<grid, 256, 0, s>>>(
+                    A, B, T, U, V, slices, EpiPartial{w.part, (size_t)rows64, T, U, slices});
+            } else {
+                joint_gemm_kernel<EpiPartial, 64, 32><<<grid, 256, 0, s>>>(
+                    A, B, T, U, V, slices, EpiPartial{w.part, (size_t)rows64, T, U, slices});
+            }
         }
         EpiStats epi{f, g, w.mf, w.mg, labels, xlen, ylen, w.inv_s, w.lp2, jd, d};
         joint_stats_kernel<<<(d.rows + 255) / 256, 256, 0, s>>>(w.part, slices, epi);
@@ -674,7 +715,20 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     if (want_grad) {
         joint_weights_kernel<<<(d.rows + 255) / 256, 256, 0, s>>>(w.lp2, w.alphas, w.betas, w.llf, w.inv_s,
                                                                  xlen, ylen, w.wm, w.bk, w.lb, scale, scale_vec, d);
-        if (V >= 512) {  // long vocabulary: one thread per column, thin contraction
+        if (joint_umma_enabled()) {
+            // tcgen05, vocabulary index on the accumulator lanes (coalesced epilogue):
+            //   dF[t,v] = Ef[t,v] * sum_u Eg[u,v] Wm[t,u]      M = v, N = t, K = u
+            //   dG[u,v] = Eg[u,v] * sum_t Ef[t,v] Wm[t,u]      M = v, N = u, K = t
+            umma::Operand EgT{w.eg, (long long)U * V, 1, V, V}, EfT{w.ef, (long long)T * V, 1, V, V};
+            umma::Operand WmTU{w.wm, (long long)T * U, U, 1, T};   // (n = t, k = u): k-contiguous
+            umma::Operand WmUT{w.wm, (long long)T * U, 1, U, U};   // (n = u, k = t): n-contiguous
+            // 64-column accumulator tiles: small tensor-memory / shared-memory footprint -> several CTAs per SM,
+            // and the whole tile's Ef fetches are in flight before the accumulator is read
+            launch_umma<0, 1, 24>(EgT, WmTU, V, T, U, 1, N,
+                                  umma::Epilogue{w.ef, (long long)T * V, 1, V, dF, 0, (long long)T * V, 1, V}, s, 64);
+            launch_umma<0, 0, 24>(EfT, WmUT, V, U, T, 1, N,
+                                  umma::Epilogue{w.eg, (long long)U * V, 1, V, dG, 0, (long long)U * V, 1, V}, s);
+        } else if (V >= 512) {  // long vocabulary: one thread per column, thin contraction
             {   // dF[t,v] = Ef[t,v] * sum_u Wm[t,u] Eg[u,v]
                 dim3 grid((V + 255) / 256, (T + kJointRT - 1) / kJointRT, N);
                 joint_thin_kernel<<<grid, 256, 0, s>>>(w.wm, U, 1, (size_t)T * U, w.eg, w.ef, dF, T, U, V);

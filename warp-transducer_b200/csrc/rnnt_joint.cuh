@@ -19,6 +19,7 @@
 #pragma once
 #include "rnnt_kernels.cuh"
 #include "rnnt_lattice.cuh"
+#include "rnnt_umma.cuh"
 
 namespace b200rnnt {
 

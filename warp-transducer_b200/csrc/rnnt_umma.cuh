@@ -14,17 +14,16 @@
 // each k-step issues three MMAs into the same accumulator: hi*hi + hi*lo + lo*hi.  The dropped lo*lo
 // term is 2^-22 relative; the sums feed a logarithm (S) and gradients checked to 1e-4 (P, Q).
 //
-// Operands are staged global -> registers (split) -> shared memory in the UMMA canonical NO-SWIZZLE
-// ("interleave") layouts, in units of 16-byte chunks (cute/atom/mma_traits_sm100.hpp:167-203):
-//   K-major  : ((8,n),2):((1,SBO),LBO)          element (mn,k) at (mn%8)*16 + (mn/8)*SBO + (k/4)*LBO + (k%4)*4
-//   MN-major : ((1,n),(8,k)):((X,SBO),(1,LBO))  element (mn,k) at (mn%4)*4 + (mn/4)*SBO + (k%8)*16 + (k/8)*LBO
-// so whichever index is contiguous in global memory stays contiguous in shared memory and no transpose
-// is ever needed.  The strides are padded (144 B instead of 128 B) so the scalar stores of a warp hit
-// 32 different banks.
+// Operands are staged global -> registers (split) -> shared memory in the UMMA canonical K-major
+// NO-SWIZZLE ("interleave") layout, in units of 16-byte chunks (cute/atom/mma_traits_sm100.hpp:190-203):
+//   ((8,n),2):((1,SBO),LBO)     element (mn,k) at (mn%8)*16 + (mn/8)*SBO + (k/4)*LBO + (k%4)*4
+// (verified element by element on a B200 with tools/probe/umma_layout_probe.cu).  The chunk stride is
+// padded (144 B instead of 128 B) so that the scalar stores of a warp hit 32 different banks.
 //
-// One CTA = 128 threads = 4 warps = the 4 lane quarters of the 128-lane accumulator.  All threads
-// produce a k-stage, thread 0 issues its MMAs and commits them to an mbarrier, everybody waits for the
-// commit before the stage buffers are overwritten; the epilogue reads the accumulator with tcgen05.ld.
+// One CTA = 256 threads = 8 warps, two per lane quarter of the 128-lane accumulator.  All threads
+// produce the k-stages (double-buffered, next stage's loads in flight in registers), thread 0 issues the
+// MMAs of a stage and commits them to that buffer's mbarrier; the epilogue reads the accumulator with
+// tcgen05.ld.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,9 +62,9 @@ __device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done)
-                     : "r"(bar), "r"(parity)
+                     : "r"(bar), "r"(parity), "r"(1000u)
                      : "memory");
 }
 // 16 consecutive fp32 columns of this thread's accumulator lane
@@ -95,33 +94,26 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N, bool a_mn, 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int kPad = 144;   // padded 16-byte-chunk group stride: 8 chunks (128 B) + one chunk of padding
+constexpr int kPad = 144;   // padded stride between the 16-byte k-chunks of a row group: 8 chunks (128 B) + 16 B
 
-// Geometry of one operand tile [MN x KS] in shared memory.
-template <bool MN_MAJOR> struct TileGeom;
-template <> struct TileGeom<false> {   // K-major
-    // chunk (mn/8, k/4) of 8 rows x 16 B; k-chunks kPad apart, 8-row groups (KS/4)*kPad apart
-    static __host__ __device__ constexpr uint32_t lbo(int /*MN*/, int /*KS*/) { return kPad; }
-    static __host__ __device__ constexpr uint32_t sbo(int /*MN*/, int KS) { return (uint32_t)(KS / 4) * kPad; }
-    static __host__ __device__ constexpr uint32_t bytes(int MN, int KS) { return (uint32_t)(MN / 8) * sbo(MN, KS); }
-    static __device__ __forceinline__ uint32_t off(int mn, int k, int MN, int KS) {
-        return (uint32_t)(mn & 7) * 16 + (uint32_t)(mn >> 3) * sbo(MN, KS) + (uint32_t)(k >> 2) * kPad + (uint32_t)(k & 3) * 4;
+// Geometry of one operand tile [MN x KS] in shared memory: K-major, no swizzle.  Chunk (mn/8, k/4) holds
+// 8 rows x 16 B; the k-chunks of a row group are kPad apart (LBO), row groups (KS/4)*kPad apart (SBO).
+// (MN-major tf32 operands were tried: tcgen05.mma kind::tf32 returns zeros for them in the no-swizzle
+//  layouts on sm_100a - tools/probe/umma_layout_probe.cu - so operands that are MN-contiguous in global
+//  memory are transposed on their way into shared memory instead.)
+struct TileGeom {
+    static __host__ __device__ constexpr uint32_t lbo() { return kPad; }
+    static __host__ __device__ constexpr uint32_t sbo(int KS) { return (uint32_t)(KS / 4) * kPad; }
+    static __host__ __device__ constexpr uint32_t bytes(int MN, int KS) { return (uint32_t)(MN / 8) * sbo(KS); }
+    static __device__ __forceinline__ uint32_t off(int mn, int k, int KS) {
+        return (uint32_t)(mn & 7) * 16 + (uint32_t)(mn >> 3) * sbo(KS) + (uint32_t)(k >> 2) * kPad + (uint32_t)(k & 3) * 4;
     }
     // descriptor start offset of k-step j (8 values of k = two 16-byte chunks)
-    static __host__ __device__ constexpr uint32_t kstep(int j, int /*MN*/, int /*KS*/) { return (uint32_t)(2 * j) * kPad; }
-};
-template <> struct TileGeom<true> {    // MN-major
-    // chunk (mn/4, k/8) of 8 k-rows x 16 B; mn-chunks kPad apart, k-groups (MN/4)*kPad apart
-    static __host__ __device__ constexpr uint32_t sbo(int /*MN*/, int /*KS*/) { return kPad; }
-    static __host__ __device__ constexpr uint32_t lbo(int MN, int /*KS*/) { return (uint32_t)(MN / 4) * kPad; }
-    static __host__ __device__ constexpr uint32_t bytes(int MN, int KS) { return (uint32_t)(KS / 8) * lbo(MN, KS); }
-    static __device__ __forceinline__ uint32_t off(int mn, int k, int MN, int KS) {
-        return (uint32_t)(mn & 3) * 4 + (uint32_t)(mn >> 2) * kPad + (uint32_t)(k & 7) * 16 + (uint32_t)(k >> 3) * lbo(MN, KS);
-    }
-    static __host__ __device__ constexpr uint32_t kstep(int j, int MN, int KS) { return (uint32_t)j * lbo(MN, KS); }
+    static __host__ __device__ constexpr uint32_t kstep(int j) { return (uint32_t)(2 * j) * kPad; }
 };
 
-// element (mn, k) of batch b lives at p + b*batch + mn*s_mn + k*s_k; rows mn >= mn_valid and columns k >= k_valid read as 0
+// element (mn, k) of batch b lives at p + b*batch + mn*s_mn + k*s_k (one of the two strides is 1);
+// rows mn >= mn_valid and columns k >= the slice end read as 0
 struct Operand {
     const float* p;
     long long batch;
@@ -136,109 +128,229 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-// Fill one stage of an operand: tile rows [mn0, mn0+MN), k in [k0, k0+KS), hi and lo copies.
-// The thread index runs along the index that is contiguous in GLOBAL memory, so loads coalesce.
-template <bool MN_MAJOR, int MN, int KS>
-__device__ __forceinline__ void fill_stage(unsigned char* hi, unsigned char* lo, const Operand& op, const float* base,
-                                           int mn0, int k0, int k_end) {
-    using G = TileGeom<MN_MAJOR>;
-    for (int i = threadIdx.x; i < MN * KS; i += blockDim.x) {
-        int mn, k;
-        if (MN_MAJOR) { mn = i % MN; k = i / MN; } else { k = i % KS; mn = i / KS; }
-        float x = 0.0f;
-        if (mn0 + mn < op.mn_valid && k0 + k < k_end)
-            x = __ldg(base + (long long)(mn0 + mn) * op.s_mn + (long long)(k0 + k) * op.s_k);
-        float h, l;
-        split_tf32(x, h, l);
-        const uint32_t o = G::off(mn, k, MN, KS);
-        *reinterpret_cast<float*>(hi + o) = h;
-        *reinterpret_cast<float*>(lo + o) = l;
-    }
-}
+// One operand's share of a k-stage, staged through registers.  init() fixes, once per CTA, this
+// thread's first element (global pointer, shared-memory offset) - every further element of the thread is a
+// COMPILE-TIME step away in shared memory and a constant stride away in global memory, so the stage loop
+// carries no index arithmetic.  load() issues all of the thread's global loads for the stage at k0 (they
+// stay in flight while the previous stage is multiplied), store() splits into hi / lo and writes the two
+// shared-memory copies.
+//  MODE 2 (k-contiguous, 16-byte aligned rows): float4 loads, one 16-byte chunk per store (KS in {8,16,32,64}).
+//  MODE 1 (k-contiguous, unaligned rows, KS <= 32): scalar; lane = k, warp = row.
+//  MODE 0 (mn-contiguous): scalar; a warp covers 8 consecutive mn x 4 consecutive k - four full 32-byte
+//         sectors per load instruction, 32 different banks per store (the transposition happens here).
+constexpr int kThreads = 256;   // 8 warps: two per accumulator lane quarter (they split the columns in the epilogue)
+template <int MODE, int MN, int KS> struct StageRegs {
+    static constexpr int CH = KS / 4;                 // 16-byte chunks per row
+    static constexpr int RP = kThreads / (CH > 0 ? CH : 1);   // MODE 2: rows per pass
+    static constexpr int MB = MN / 8;                 // MODE 0: 8-row blocks per k-group
+    static constexpr int Q = MB >= 8 ? MB / 8 : 1;    // MODE 0, MB >= 8: passes over mn per k-group
+    static constexpr int KB_STEP = MB >= 8 ? 1 : 8 / MB;   // MODE 0: k-groups advanced per pass (MB < 8: several at once)
+    static constexpr int PER = MODE == 2 ? (MN + RP - 1) / RP : MODE == 1 ? MN / 8 : MB >= 8 ? Q * CH : (CH + KB_STEP - 1) / KB_STEP;
+    static_assert(MODE != 2 || (kThreads % CH == 0 && RP % 8 == 0), "MODE 2 needs KS in {8,16,32,64}");
+    static_assert(MODE != 1 || KS <= 32, "MODE 1 needs KS <= 32");
+    static_assert(MODE != 0 || (MB >= 8 ? MB % 8 == 0 : 8 % MB == 0), "MODE 0 needs MN in {8,16,32,64} or a multiple of 64");
 
-// D[128 x N] = sum_{k in [kbeg,kend)} A[m0+m][k] * B[n][k]   for batch blockIdx.z, M tile blockIdx.y,
-// k slice blockIdx.x.  Epi(b, slice, m (global row), n, value) is called for every element with m < A.mn_valid
-// and n < B.mn_valid.
-template <bool A_MN, bool B_MN, int N, int KS, typename Epi>
-__global__ void __launch_bounds__(128)
-gemm_kernel(const Operand A, const Operand B, int K, int slices, const Epi epi, const int variant = 0) {
-    static_assert(N % 16 == 0 && N >= 16 && N <= 256 && KS % 8 == 0, "UMMA shape");
-    using GA = TileGeom<A_MN>;
-    using GB = TileGeom<B_MN>;
-    constexpr uint32_t A_BYTES = GA::bytes(128, KS), B_BYTES = GB::bytes(N, KS);
+    float4 v4[MODE == 2 ? PER : 1];
+    float v1[MODE == 2 ? 1 : PER];
+    const float* g0;      // this thread's element 0 at k0 = 0
+    long long g_mn, g_k;  // global strides (elements) along mn / k
+    uint32_t o0;          // shared-memory offset of element 0
+    int mn_first, k_first, mn_lim;
+
+    __device__ __forceinline__ void init(const Operand& op, const float* base, int mn0) {
+        const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+        g_mn = op.s_mn, g_k = op.s_k;
+        if (MODE == 2) {
+            mn_first = tid / CH;
+            k_first = 4 * (tid % CH);
+        } else if (MODE == 1) {
+            mn_first = w;
+            k_first = lane;
+        } else {
+            const int mm = tid & 7, kk = (tid >> 3) & 3;
+            mn_first = (MB >= 8 ? w : w % MB) * 8 + mm;
+            k_first = (MB >= 8 ? 0 : w / MB) * 4 + kk;
+        }
+        o0 = TileGeom::off(mn_first, k_first, KS);
+        g0 = base + (long long)(mn0 + mn_first) * g_mn + (long long)k_first * g_k;
+        mn_lim = op.mn_valid - mn0 - mn_first;   // element j is a real row iff its mn step < mn_lim
+    }
+    // (mn step, k step) of element j relative to element 0 - compile-time
+    static __device__ __forceinline__ constexpr int dmn(int j) {
+        return MODE == 2 ? j * RP : MODE == 1 ? 8 * j : MB >= 8 ? 64 * (j % Q) : 0;
+    }
+    static __device__ __forceinline__ constexpr int dk(int j) {
+        return MODE == 2 ? 0 : MODE == 1 ? 0 : MB >= 8 ? 4 * (j / Q) : 4 * KB_STEP * j;
+    }
+    __device__ __forceinline__ void load(int k0, int k_end) {
+        const float* g = g0 + (long long)k0 * g_k;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int kj = k0 + k_first + dk(j);
+            const bool in = dmn(j) < mn_lim && kj < k_end && (MODE != 1 || k_first < KS) &&
+                            (MODE == 2 ? mn_first + dmn(j) < MN : k_first + dk(j) < KS);
+            const float* p = g + (long long)dmn(j) * g_mn + (long long)dk(j) * g_k;
+            if (MODE == 2) {
+                v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (in) {
+                    if (kj + 3 < k_end) {
+                        v4[j] = __ldg(reinterpret_cast<const float4*>(p));
+                    } else {   // ragged end of the k range
+                        v4[j].x = __ldg(p);
+                        if (kj + 1 < k_end) v4[j].y = __ldg(p + 1);
+                        if (kj + 2 < k_end) v4[j].z = __ldg(p + 2);
+                    }
+                }
+            } else {
+                v1[j] = in ? __ldg(p) : 0.0f;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(unsigned char* hi, unsigned char* lo) const {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            // offset step of element j: row groups are SBO apart, k-chunks kPad apart (compile-time)
+            const uint32_t o = o0 + (uint32_t)(dmn(j) / 8) * TileGeom::sbo(KS) + (uint32_t)(dk(j) / 4) * kPad;
+            const bool slot = (MODE == 2 ? mn_first + dmn(j) < MN : k_first + dk(j) < KS) && (MODE != 1 || k_first < KS);
+            if (slot) {
+                if (MODE == 2) {
+                    float4 h, l;
+                    split_tf32(v4[j].x, h.x, l.x);
+                    split_tf32(v4[j].y, h.y, l.y);
+                    split_tf32(v4[j].z, h.z, l.z);
+                    split_tf32(v4[j].w, h.w, l.w);
+                    *reinterpret_cast<float4*>(hi + o) = h;
+                    *reinterpret_cast<float4*>(lo + o) = l;
+                } else {
+                    float h, l;
+                    split_tf32(v1[j], h, l);
+                    *reinterpret_cast<float*>(hi + o) = h;
+                    *reinterpret_cast<float*>(lo + o) = l;
+                }
+            }
+        }
+    }
+};
+
+// What the epilogue does with accumulator element (m, n) of batch b, k slice `slice`:
+//   out[slice*out_s + b*out_b + m*out_m + n*out_n] = acc * (in ? in[b*in_b + m*in_m + n*in_n] : 1)
+// The `in` values of a group of columns are fetched before the accumulator is waited for.
+struct Epilogue {
+    const float* in;
+    long long in_b, in_m, in_n;
+    float* out;
+    long long out_s, out_b, out_m, out_n;
+};
+
+// D[128 x N] = sum_{k in slice} A[m0+m][k] * B[n0+n][k]   for batch blockIdx.z, M tile blockIdx.y, and
+// blockIdx.x = k slice + slices * N tile.  A_MODE / B_MODE: how the operand is fetched (StageRegs).
+// One shared-memory stage buffer per CTA (kBufs): the footprint stays small, so 4-6 CTAs are resident per SM
+// and cover each other's load -> split -> multiply chains; within a CTA the global loads of stage s+1 are in
+// flight in registers while stage s is multiplied.  Elements with m >= A.mn_valid or n >= B.mn_valid are skipped.
+constexpr int kBufs = 1;
+template <int A_MODE, int B_MODE, int N, int KS>
+__global__ void __launch_bounds__(kThreads, 3)
+gemm_kernel(const Operand A, const Operand B, int K, int slices, const Epilogue epi) {
+    static_assert(N % 32 == 0 && N >= 32 && N <= 256 && KS % 8 == 0, "UMMA shape (two epilogue warps per lane quarter)");
+    constexpr uint32_t A_BYTES = TileGeom::bytes(128, KS), B_BYTES = TileGeom::bytes(N, KS);
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* a_hi = smem;
-    unsigned char* a_lo = a_hi + A_BYTES;
-    unsigned char* b_hi = a_lo + A_BYTES;
-    unsigned char* b_lo = b_hi + B_BYTES;
-    __shared__ __align__(8) unsigned long long mma_done;
+    __shared__ __align__(8) unsigned long long mma_done[2];
     __shared__ uint32_t tmem_base_slot;
 
-    const int b = blockIdx.z, m0 = blockIdx.y * 128, slice = blockIdx.x;
+    const int b = blockIdx.z, m0 = blockIdx.y * 128, slice = blockIdx.x % slices, n0 = (blockIdx.x / slices) * N;
     const int kper = ((K + slices - 1) / slices + KS - 1) / KS * KS;
     const int kbeg = slice * kper, kend = min(K, kbeg + kper);
+    const int nstages = kbeg < kend ? (kend - kbeg + KS - 1) / KS : 0;
     const int warp = threadIdx.x >> 5;
 
+    StageRegs<A_MODE, 128, KS> ra;
+    StageRegs<B_MODE, N, KS> rb;
+    ra.init(A, A.p + (long long)b * A.batch, m0);
+    rb.init(B, B.p + (long long)b * B.batch, n0);
+    if (nstages > 0) {   // first stage's loads go out before anything else
+        ra.load(kbeg, kend);
+        rb.load(kbeg, kend);
+    }
     if (warp == 0) tmem_alloc(s32(&tmem_base_slot), TMEM_COLS);
-    if (threadIdx.x == 0) bar_init(s32(&mma_done), 1);
+    if (threadIdx.x == 0) {
+        bar_init(s32(&mma_done[0]), 1);
+        bar_init(s32(&mma_done[1]), 1);
+    }
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem_d = tmem_base_slot;
-    const uint32_t idesc = instr_desc_tf32(128, N, A_MN, B_MN);
-    const float* abase = A.p + (long long)b * A.batch;
-    const float* bbase = B.p + (long long)b * B.batch;
+    constexpr uint32_t idesc = instr_desc_tf32(128, N, false, false);
 
-    uint32_t parity = 0, accum = 0;
-    for (int k0 = kbeg; k0 < kend; k0 += KS) {
-        fill_stage<A_MN, 128, KS>(a_hi, a_lo, A, abase, m0, k0, kend);
-        fill_stage<B_MN, N, KS>(b_hi, b_lo, B, bbase, 0, k0, kend);
+    for (int s = 0; s < nstages; ++s) {
+        const int buf = s % kBufs;
+        unsigned char* a_hi = smem + buf * STAGE_BYTES;
+        unsigned char* a_lo = a_hi + A_BYTES;
+        unsigned char* b_hi = a_lo + A_BYTES;
+        unsigned char* b_lo = b_hi + B_BYTES;
+        // the MMAs of the stage that last used this buffer have finished reading it
+        if (s >= kBufs) bar_wait(s32(&mma_done[buf]), (uint32_t)(((s - kBufs) / kBufs) & 1));
+        ra.store(a_hi, a_lo);
+        rb.store(b_hi, b_lo);
+        if (s + 1 < nstages) {   // next stage's loads fly during the barrier and the MMAs
+            ra.load(kbeg + (s + 1) * KS, kend);
+            rb.load(kbeg + (s + 1) * KS, kend);
+        }
         fence_smem_async();      // generic-proxy stores -> visible to the tensor core's async proxy
         __syncthreads();
         if (threadIdx.x == 0) {
             fence_after();
 #pragma unroll
             for (int j = 0; j < KS / 8; ++j) {
-                // (variant bits: probe-only switches that swap the two stride fields of a descriptor)
-                const uint32_t al_ = (variant & 1) ? GA::sbo(128, KS) : GA::lbo(128, KS), as_ = (variant & 1) ? GA::lbo(128, KS) : GA::sbo(128, KS);
-                const uint32_t bl_ = (variant & 2) ? GB::sbo(N, KS) : GB::lbo(N, KS), bs_ = (variant & 2) ? GB::lbo(N, KS) : GB::sbo(N, KS);
-                const uint64_t ah = smem_desc(s32(a_hi) + GA::kstep(j, 128, KS), al_, as_);
-                const uint64_t al = smem_desc(s32(a_lo) + GA::kstep(j, 128, KS), al_, as_);
-                const uint64_t bh = smem_desc(s32(b_hi) + GB::kstep(j, N, KS), bl_, bs_);
-                const uint64_t bl = smem_desc(s32(b_lo) + GB::kstep(j, N, KS), bl_, bs_);
-                mma_tf32(tmem_d, ah, bh, idesc, accum);
+                const uint64_t ah = smem_desc(s32(a_hi) + TileGeom::kstep(j), TileGeom::lbo(), TileGeom::sbo(KS));
+                const uint64_t al = smem_desc(s32(a_lo) + TileGeom::kstep(j), TileGeom::lbo(), TileGeom::sbo(KS));
+                const uint64_t bh = smem_desc(s32(b_hi) + TileGeom::kstep(j), TileGeom::lbo(), TileGeom::sbo(KS));
+                const uint64_t bl = smem_desc(s32(b_lo) + TileGeom::kstep(j), TileGeom::lbo(), TileGeom::sbo(KS));
+                mma_tf32(tmem_d, ah, bh, idesc, (s | j) != 0);
                 mma_tf32(tmem_d, ah, bl, idesc, 1);
                 mma_tf32(tmem_d, al, bh, idesc, 1);
-                accum = 1;
             }
-            mma_commit(s32(&mma_done));
+            mma_commit(s32(&mma_done[buf]));
         }
-        bar_wait(s32(&mma_done), parity);   // the stage buffers are free again (and, last time, D is complete)
-        parity ^= 1;
     }
-    fence_after();
 
-    // epilogue: warp w owns accumulator lanes [32w, 32w+32); lane = row m of the tile
-    const int m = m0 + warp * 32 + (threadIdx.x & 31);
+    // epilogue: warps w and w+4 own accumulator lanes [32(w%4), +32) and one half of the columns each;
+    // lane = row m of the tile.  The `in` values of a group of 16 columns are fetched before the accumulator
+    // is waited for / read; all addresses are a base plus a running stride.
+    const int quarter = warp & 3, half = warp >> 2;
+    const int m = m0 + quarter * 32 + (threadIdx.x & 31);
+    const bool mrow = m < A.mn_valid;
+    constexpr int HALF = N / 2;
+    const float* ip = epi.in ? epi.in + b * epi.in_b + m * epi.in_m + (long long)(n0 + half * HALF) * epi.in_n : nullptr;
+    float* op = epi.out + slice * epi.out_s + b * epi.out_b + m * epi.out_m + (long long)(n0 + half * HALF) * epi.out_n;
+    const int nlim = B.mn_valid - n0 - half * HALF;   // columns of this half that exist
+    bool waited = false;
 #pragma unroll 1
-    for (int c0 = 0; c0 < N; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-        if (kbeg < kend || true) {
+    for (int c = 0; c < HALF; c += 16) {
+        float pre[16], v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (m < A.mn_valid && c0 + i < B.mn_valid) epi(b, slice, m, c0 + i, kbeg < kend ? v[i] : 0.0f);
+        for (int i = 0; i < 16; ++i) pre[i] = (ip && mrow && c + i < nlim) ? __ldg(ip + (long long)(c + i) * epi.in_n) : 1.0f;
+        if (!waited) {
+            // commits complete in issue order: the last stage's barrier covers all of them
+            if (nstages > 0) bar_wait(s32(&mma_done[(nstages - 1) % kBufs]), (uint32_t)(((nstages - 1) / kBufs) & 1));
+            fence_after();
+            waited = true;
         }
+        tmem_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * HALF + c), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (mrow && c + i < nlim) op[(long long)(c + i) * epi.out_n] = nstages > 0 ? v[i] * pre[i] : 0.0f;
     }
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
-template <bool A_MN, bool B_MN, int N, int KS>
-constexpr size_t gemm_smem_bytes() {
-    return 2 * (size_t)TileGeom<A_MN>::bytes(128, KS) + 2 * (size_t)TileGeom<B_MN>::bytes(N, KS);
+template <int N, int KS>
+constexpr size_t gemm_smem_bytes() {   // kBufs stage buffers, each with hi and lo copies of both operand tiles
+    return kBufs * (2 * (size_t)TileGeom::bytes(128, KS) + 2 * (size_t)TileGeom::bytes(N, KS));
 }
 
 }  // namespace umma
