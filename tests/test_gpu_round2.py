@@ -131,3 +131,35 @@ def test_forward_backward_likelihoods_agree(wr):
     llf, llb = wr.read_log_likelihoods(ws, 30, 9, 4, 4)
     assert np.allclose(llf, llb, rtol=1e-6, atol=1e-4), (llf, llb)
     assert np.allclose(-llf, costs.cpu().numpy(), rtol=1e-6)
+
+
+def test_tensorflow_op_call_sequence(wr, known_answers):
+    """The TensorFlow GPU kernel's exact calls (tensorflow_binding/src/warprnnt_op.cc:97-129,173-187):
+    options = rnntOptions{} with only loc / stream / blank_label / maxT / maxU set (batch_first stays
+    false), get_workspace_size with the default dtype size, device acts / grads / labels / lengths, and
+    `costs` in HOST memory (.HostMemory("costs")), readable when the call returns.  Checked against the
+    vectors of tensorflow_binding/tests/test_warprnnt_op.py:68-79."""
+    import ctypes as C
+    ka = known_answers["options"]
+    a = np.array(ka["acts"], np.float32).reshape(ka["shape"])
+    N, T, U, V = a.shape
+    dev = torch.device("cuda:0")
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        acts = torch.as_tensor(a).to(dev)
+        grads = torch.full_like(acts, float("nan"))
+        labels = torch.as_tensor(np.array(ka["labels"], np.int32)).to(dev)
+        tl = torch.full((N,), T, dtype=torch.int32, device=dev)
+        ul = torch.full((N,), U - 1, dtype=torch.int32, device=dev)
+    stream.synchronize()
+    opt = wr.rnntOptions()                      # zero-initialised, as `auto options = rnntOptions{}`
+    opt.loc, opt.stream, opt.blank_label, opt.maxT, opt.maxU = 1, stream.cuda_stream, 0, T, U
+    nbytes = C.c_size_t(0)
+    assert wr.lib().get_workspace_size(T, U, N, True, C.byref(nbytes), 4) == 0
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)      # ctx->allocate_temp
+    costs = np.full(N, np.nan, np.float32)                             # host memory
+    st = wr.lib().compute_rnnt_loss(acts.data_ptr(), grads.data_ptr(), labels.data_ptr(), ul.data_ptr(),
+                                    tl.data_ptr(), V, N, costs.ctypes.data, ws.data_ptr(), opt)
+    assert st == 0
+    assert np.allclose(costs, ka["costs"], atol=1e-6)                  # readable right after the call
+    assert np.allclose(grads.cpu().numpy().reshape(-1), ka["logits_grads"], atol=1e-6)   # the TF test's tolerance

@@ -125,14 +125,35 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
     }
 
     const T* x = tile + (valid ? i : 0) * V;   // rows that are not valid walk row 0 (results discarded)
+    // Even V: the row is walked as PAIRS (one 8/16-byte shared-memory access per two elements) - half the
+    // load instructions of an issue-bound kernel; the row start i*V is pair-aligned because V is even.
+    using Pair = typename R::pair;
+    const bool paired = (V & 1) == 0;
+    const Pair* x2 = reinterpret_cast<const Pair*>(x);
     T m = R::neg_inf();
+    if (paired) {
 #pragma unroll 4
-    for (int k = h; k < V; k += TPR) m = R::max(m, x[k]);
+        for (int p = h; p < (V >> 1); p += TPR) {
+            const Pair v = x2[p];
+            m = R::max(m, R::max(v.x, v.y));
+        }
+    } else {
+#pragma unroll 4
+        for (int k = h; k < V; k += TPR) m = R::max(m, x[k]);
+    }
     const T M = group_max<TPR>(m);
     const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
     T s = 0;
+    if (paired) {
 #pragma unroll 4
-    for (int k = h; k < V; k += TPR) s += es.term(x[k]);
+        for (int p = h; p < (V >> 1); p += TPR) {
+            const Pair v = x2[p];
+            s += es.term(v.x) + es.term(v.y);
+        }
+    } else {
+#pragma unroll 4
+        for (int k = h; k < V; k += TPR) s += es.term(x[k]);
+    }
     const T S = group_sum<TPR>(s);
     if (valid && h == 0) {
         const T lse = es.log_of(S);
@@ -231,12 +252,25 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
         xy = x[rg.y >= 0 ? rg.y : 0];
     }
     __syncwarp();
+    using Pair = typename R::pair;
+    Pair* x2 = reinterpret_cast<Pair*>(x);
     if (valid) {
+        if ((V & 1) == 0) {   // pairs: one shared-memory load and one store per two elements
 #pragma unroll 4
-        for (int k = h; k < V; k += TPR) {
-            T g = R::exp2(fma(x[k] - rg.m, (T)R::kLog2e, rg.cA));
-            if (SCALED) g *= scale;
-            x[k] = g;
+            for (int p = h; p < (V >> 1); p += TPR) {
+                Pair v = x2[p];
+                v.x = R::exp2(fma(v.x - rg.m, (T)R::kLog2e, rg.cA));
+                v.y = R::exp2(fma(v.y - rg.m, (T)R::kLog2e, rg.cA));
+                if (SCALED) v.x *= scale, v.y *= scale;
+                x2[p] = v;
+            }
+        } else {
+#pragma unroll 4
+            for (int k = h; k < V; k += TPR) {
+                T g = R::exp2(fma(x[k] - rg.m, (T)R::kLog2e, rg.cA));
+                if (SCALED) g *= scale;
+                x[k] = g;
+            }
         }
     } else if (inrange) {
         for (int k = h; k < V; k += TPR) x[k] = T(0);

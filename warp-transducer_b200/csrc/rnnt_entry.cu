@@ -667,8 +667,18 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
 
     if (phase != kBackward) {
     // J1: factor-wise max and exponentials
-    joint_prep_kernel<<<(N * T + 7) / 8, 256, 0, s>>>(f, w.ef, w.mf, N * T, V);
-    joint_prep_kernel<<<(N * U + 7) / 8, 256, 0, s>>>(g, w.eg, w.mg, N * U, V);
+    auto prep = [&](const float* x, float* e, float* mx, int rows) {
+        const int per = (V / 4 + 255) / 256;   // float4 per thread when one CTA owns a row
+        const bool vec = V % 4 == 0 && per <= 8 && V >= 1024 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
+        if (!vec) joint_prep_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, e, mx, rows, V);
+        else if (per <= 1) joint_prep_row_kernel<1><<<rows, 256, 0, s>>>(x, e, mx, V);
+        else if (per <= 2) joint_prep_row_kernel<2><<<rows, 256, 0, s>>>(x, e, mx, V);
+        else if (per <= 4) joint_prep_row_kernel<4><<<rows, 256, 0, s>>>(x, e, mx, V);
+        else if (per <= 5) joint_prep_row_kernel<5><<<rows, 256, 0, s>>>(x, e, mx, V);
+        else joint_prep_row_kernel<8><<<rows, 256, 0, s>>>(x, e, mx, V);
+    };
+    prep(f, w.ef, w.mf, N * T);
+    prep(g, w.eg, w.mg, N * U);
     // J2: S = Ef . Eg^T in kJointSlices deterministic K-slabs, then lse + lattice log-prob pairs
     {
         const int slices = joint_slices(V);

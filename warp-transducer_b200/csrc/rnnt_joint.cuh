@@ -44,6 +44,47 @@ joint_prep_kernel(const float* __restrict__ x, float* __restrict__ e, float* __r
     if (lane == 0) mx[row] = m;
 }
 
+// Same, one CTA per row with the whole row in registers (V % 4 == 0, V <= 256*4*NV): the factor is read
+// ONCE (16-byte loads, all in flight before first use) and its exponentials written once with 16-byte
+// stores - the streaming shape of rowstats_row_kernel.
+template <int NV>
+__global__ void __launch_bounds__(256)
+joint_prep_row_kernel(const float* __restrict__ x, float* __restrict__ e, float* __restrict__ mx, int V) {
+    __shared__ float sh[8];
+    const int row = blockIdx.x, nv = V >> 2;
+    const float4* p = reinterpret_cast<const float4*>(x + (size_t)row * V);
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i = threadIdx.x + j * 256;
+        v[j] = i < nv ? __ldg(p + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) m = fmaxf(m, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+    m = group_max<32>(m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = sh[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sh[w]);
+    const float mz = (m == -INFINITY) ? 0.0f : m;
+    float4* q = reinterpret_cast<float4*>(e + (size_t)row * V);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i = threadIdx.x + j * 256;
+        if (i < nv) {
+            float4 o;
+            o.x = Real<float>::exp(v[j].x - mz);
+            o.y = Real<float>::exp(v[j].y - mz);
+            o.z = Real<float>::exp(v[j].z - mz);
+            o.w = Real<float>::exp(v[j].w - mz);
+            q[i] = o;
+        }
+    }
+    if (threadIdx.x == 0) mx[row] = m;
+}
+
 // ---- generic batched fp32 GEMM  C[b](m,n) = sum_k A[b](m,k) * B[b](k,n), strided operands ----------
 // 64x64 tile, 16-deep k-chunks through shared memory, 256 threads x (4x4) outputs.  Epilogue
 // functor Epi(b, m, n, acc) writes the result.

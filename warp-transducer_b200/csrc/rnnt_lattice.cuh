@@ -116,11 +116,25 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
     const float4* gp = fac + base + u + (ptrdiff_t)n0 * mU;  // next diagonal to fetch
     LogVal* sp = out + base + u + (ptrdiff_t)n0 * mU;
     int nu = n0 - u;                                     // (current diagonal) - u: active iff (unsigned)nu < width
+    // Ring slots that no copy will fill hold NEUTRAL factors: the step body below runs unconditionally - a
+    // column that is not active yet keeps its "log zero" unchanged, a column that has finished computes
+    // values nobody reads - and only the lattice STORE is predicated.
 #pragma unroll
-    for (int k = 0; k < kLinRing - 1; ++k) {
-        if ((unsigned)(nu + k * DIR) < width) cp_async16_s(ring_u + k * step_bytes, gp);
-        cp_async_commit();
-        gp += dstep;
+    for (int k = 0; k < kLinRing; ++k) {
+        if (k < kLinRing - 1 && (unsigned)(nu + k * DIR) < width) {
+            cp_async16_s(ring_u + k * step_bytes, gp);
+        } else if (k < kLinRing - 1 || !((unsigned)(nu + k * DIR) < width)) {   // (the last slot is step 0's refill target)
+            // {m_blank, k_blank, m_label, k_label} = {1, 0, 1, log zero}: the "stay" factor is the identity, the
+            // "emit" factor kills the neighbour's contribution (beta's virtual beta(T,U-1) = 1 sits in column
+            // U-1 from the start and must not leak into column U-2 before that column becomes active)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %1, %3};" ::"r"(ring_u + k * step_bytes), "r"(0x3f800000), "r"(0),
+                         "r"(kEZero)
+                         : "memory");
+        }
+        if (k < kLinRing - 1) {
+            cp_async_commit();
+            gp += dstep;
+        }
     }
     // running value.  alpha: (sv,se) = alpha(t,u) p_blank(t,u) offered to (t+1,u), (ov,oe) = alpha(t,u)
     // p_label(t,u) offered to (t,u+1).  beta: (sv,se) = beta(t+1,u).
@@ -134,6 +148,7 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
     const bool has_dst = MULTI && (BACKWARD ? warp > 0 : warp + 1 < nactive);
     const bool edge_lane = BACKWARD ? lane == 31 : lane == 0;   // the lane without a neighbour inside the warp
     const bool pub_lane = BACKWARD ? lane == 0 : lane == 31;    // the lane whose value the next warp needs
+    const int edge_bias = edge_lane ? kEZero : 0;
     const uint32_t src_edge = edge_base + (BACKWARD ? warp + 1 : warp - 1) * (kEdge * 16);
     const uint32_t my_edge = edge_base + warp * (kEdge * 16);
     const uint32_t dst_prog = prog_base + (BACKWARD ? warp - 1 : warp + 1) * 4;
@@ -158,8 +173,7 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
             cp_async_commit();
             gp += dstep;
             const bool active = (unsigned)nu < width;
-            float4 f = make_float4(1.0f, 0.0f, 1.0f, 0.0f);
-            if (active) f = lds128(ring_u + j * step_bytes);
+            const float4 f = lds128(ring_u + j * step_bytes);   // identity / stale factors when not active
 
             // neighbour's value from the previous step
             float nv;
@@ -177,11 +191,11 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
                 if (s > 0)
                     while (!pok) pok = __all_sync(0xffffffffu, edge_read(slot, s, pv, pe));
                 if (edge_lane) nv = pv, ne = pe;
-            } else if (edge_lane) {
-                nv = 1.0f, ne = kEZero;
+            } else {
+                ne += edge_bias;   // the lane without a neighbour: push its (own, shuffled-back) value to log zero
             }
-            if (active) {
-                nansum += f.x + f.z;
+            {
+                nansum = fmaf(f.x, f.z, nansum);
                 const int kb = __float_as_int(f.y), kl = __float_as_int(f.w);
                 float v;
                 int e;
@@ -195,7 +209,7 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
                     sv = v * f.x, se = e + kb;   // offered to (t+1, u)
                     ov = v * f.z, oe = e + kl;   // offered to (t, u+1)
                 }
-                *sp = to_logval(v, e);
+                if (active) *sp = to_logval(v, e);
             }
             sp += dstep;
             nu += DIR;
