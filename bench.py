@@ -479,9 +479,12 @@ def other_workloads_leg(torch, wr, dev, peaks):
         try:
             sh = Shard(torch, wr, dev, name, 7, dtype)
             small = sh.E * sh.acts.element_size() < (1 << 30)
+            ms = time_steps(torch, lambda: sh.run(wr), 10, 3, flush if small else None)
+            # per-kernel times in a second pass: the event markers between the kernels switch the
+            # programmatic-dependent-launch chaining off, so they are not part of the timed pass above
             wr.set_profiling(True)
             wr.profile_collect()
-            ms = time_steps(torch, lambda: sh.run(wr), 10, 3, flush if small else None)
+            time_steps(torch, lambda: sh.run(wr), 5, 1, flush if small else None)
             calls, kms = wr.profile_collect()
             wr.set_profiling(False)
             bytes_ = 3.0 * sh.E * sh.acts.element_size()
@@ -489,7 +492,8 @@ def other_workloads_leg(torch, wr, dev, peaks):
                         "ms_per_step": ms, "value": sh.N / (ms * 1e-3), "unit": UNIT,
                         "algorithmic_GBps": bytes_ / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": bytes_ / (ms * 1e-3) / 1e9 / hbm,
                         "frac_of_8TBps": bytes_ / (ms * 1e-3) / 1e9 / 8000.0,
-                        "kernel_ms": {"rowstats": kms[0], "lattice": kms[1], "grad": kms[2]},
+                        "kernel_ms": {"rowstats": kms[0], "lattice": kms[1], "grad": kms[2],
+                                      "note": "separate pass with event markers between the kernels (no launch overlap)"},
                         "l2": "flushed before every step" if small else "inputs exceed L2"}
             del sh
         except Exception as ex:

@@ -75,16 +75,19 @@ __device__ __forceinline__ void chunk_issue(const T* __restrict__ acts, T* tile,
 }
 
 // =================================================================================================
-// Pass 1 on a chunk: per row (max, log sum exp) and the lattice's (blank, label) log-prob pair.
+// Pass 1 on a chunk: per row (max, log sum exp) and the lattice's transition factors.
+// The CTA size NT is a template parameter: a chunk CTA is one latency chain (copy -> scalars -> walk ->
+// stores), so for very short rows more, smaller CTAs per SM keep more chains in flight.
 // =================================================================================================
-template <typename T, int TPR>
-__global__ void __launch_bounds__(ChunkThreads<T>::value)
+template <typename T, int TPR, int NT>
+__global__ void __launch_bounds__(NT)
 rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels, const int* __restrict__ xlen,
                       const int* __restrict__ ylen, typename Real<T>::pair* __restrict__ stat,
                       typename Lat<T>::fac* __restrict__ lp2, const Dims d) {
     using R = Real<T>;
-    constexpr int NT = ChunkThreads<T>::value;
-    constexpr int ROWS = NT / TPR;
+    using Pair = typename R::pair;
+    constexpr int RPT = 1;   // rows per thread group (more was measured slower, see chunk_pass())
+    constexpr int RP = NT / TPR, ROWS = RP * RPT;
     extern __shared__ __align__(128) unsigned char chunk_raw[];
     T* tile = reinterpret_cast<T*>(chunk_raw);
     __shared__ __align__(8) unsigned long long bar_store;
@@ -95,23 +98,31 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
     const bool bulk = ((nrows * (uint32_t)V * (uint32_t)sizeof(T)) & 15u) == 0;   // false only on a ragged last chunk
     // the copy goes out first: thread 0 needs nothing but the chunk index for it
     if (threadIdx.x == 0 && bulk) chunk_issue<T>(acts, tile, bar, r0, nrows, V);
+    pdl_trigger();
 
-    // per-row bookkeeping while the copy is in flight
+    // per-row bookkeeping while the copy is in flight (all rows of this thread group up front)
     const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
-    const uint32_t r = r0 + i;
-    bool valid = (uint32_t)i < nrows;
-    uint32_t u = 0, b = 0, t = 0;
-    int Ub = 0, y = -1;
-    if (valid) {
-        int Tb;
-        d.decode(r, b, t, u);
-        utt_extent(d, xlen, ylen, b, Tb, Ub);
-        valid = (int)t < Tb && (int)u < Ub;
-        if (valid && h == 0 && (int)u < Ub - 1) y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+    bool valid[RPT];
+    int y[RPT];
+    bool any = false;
+#pragma unroll
+    for (int rp = 0; rp < RPT; ++rp) {
+        const uint32_t ri = rp * RP + i;
+        valid[rp] = ri < nrows;
+        y[rp] = -1;
+        if (valid[rp]) {
+            uint32_t u, b, t;
+            int Tb, Ub;
+            d.decode(r0 + ri, b, t, u);
+            utt_extent(d, xlen, ylen, b, Tb, Ub);
+            valid[rp] = (int)t < Tb && (int)u < Ub;
+            if (valid[rp] && h == 0 && (int)u < Ub - 1) y[rp] = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+        }
+        any = any || valid[rp];
     }
     // one barrier: publishes the mbarrier to the waiters and tells whether any row of the chunk is a
     // real cell (a fully padded chunk - ragged batches only - costs one wasted read, nothing else)
-    const bool any_valid = __syncthreads_or(valid);
+    const bool any_valid = __syncthreads_or(any);
     if (!any_valid) {
         if (bulk && threadIdx.x == 0) mbar_wait(bar, 0);   // shared memory must outlive the in-flight copy
         return;
@@ -124,44 +135,51 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
         __syncthreads();
     }
 
-    const T* x = tile + (valid ? i : 0) * V;   // rows that are not valid walk row 0 (results discarded)
-    // Even V: the row is walked as PAIRS (one 8/16-byte shared-memory access per two elements) - half the
-    // load instructions of an issue-bound kernel; the row start i*V is pair-aligned because V is even.
-    using Pair = typename R::pair;
+    // Even V: a row is walked as PAIRS (one 8/16-byte shared-memory access per two elements) - half the
+    // load instructions of an issue-bound kernel; the row start is pair-aligned because V is even.
     const bool paired = (V & 1) == 0;
-    const Pair* x2 = reinterpret_cast<const Pair*>(x);
-    T m = R::neg_inf();
-    if (paired) {
+#pragma unroll
+    for (int rp = 0; rp < RPT; ++rp) {
+        const uint32_t ri = rp * RP + i;
+        const T* x = tile + (size_t)(valid[rp] ? ri : 0) * V;   // rows that are not valid walk row 0 (results discarded)
+        const Pair* x2 = reinterpret_cast<const Pair*>(x);
+        T m = R::neg_inf();
+        if (paired) {
 #pragma unroll 4
-        for (int p = h; p < (V >> 1); p += TPR) {
-            const Pair v = x2[p];
-            m = R::max(m, R::max(v.x, v.y));
+            for (int p = h; p < (V >> 1); p += TPR) {
+                const Pair v = x2[p];
+                m = R::max(m, R::max(v.x, v.y));
+            }
+        } else {
+#pragma unroll 4
+            for (int k = h; k < V; k += TPR) m = R::max(m, x[k]);
         }
-    } else {
+        const T M = group_max<TPR>(m);
+        const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
+        T s = 0;
+        if (paired) {
 #pragma unroll 4
-        for (int k = h; k < V; k += TPR) m = R::max(m, x[k]);
-    }
-    const T M = group_max<TPR>(m);
-    const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
-    T s = 0;
-    if (paired) {
+            for (int p = h; p < (V >> 1); p += TPR) {
+                const Pair v = x2[p];
+                s += es.term(v.x) + es.term(v.y);
+            }
+        } else {
 #pragma unroll 4
-        for (int p = h; p < (V >> 1); p += TPR) {
-            const Pair v = x2[p];
-            s += es.term(v.x) + es.term(v.y);
+            for (int k = h; k < V; k += TPR) s += es.term(x[k]);
         }
-    } else {
-#pragma unroll 4
-        for (int k = h; k < V; k += TPR) s += es.term(x[k]);
-    }
-    const T S = group_sum<TPR>(s);
-    if (valid && h == 0) {
-        const T lse = es.log_of(S);
-        typename R::pair st;
-        st.x = M;
-        st.y = lse;
-        stat[r] = st;
-        lp2[skew(d, b, t, u)] = Lat<T>::make((x[d.blank] - M) - lse, y >= 0 ? (x[y] - M) - lse : T(0), y >= 0);
+        const T S = group_sum<TPR>(s);
+        if (valid[rp] && h == 0) {
+            const T lse = es.log_of(S);
+            Pair st;
+            st.x = M;
+            st.y = lse;
+            const uint32_t r = r0 + ri;
+            stat[r] = st;
+            uint32_t u, b, t;
+            d.decode(r, b, t, u);
+            lp2[skew(d, b, t, u)] =
+                Lat<T>::make((x[d.blank] - M) - lse, y[rp] >= 0 ? (x[y[rp]] - M) - lse : T(0), y[rp] >= 0);
+        }
     }
 }
 
@@ -170,16 +188,17 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
 // constants as grad_row_kernel (rnnt_kernels.cuh); the blank / label corrections are applied to the
 // two affected words of the row after the sweep.
 // =================================================================================================
-template <typename T, int TPR, bool SCALED>
-__global__ void __launch_bounds__(ChunkThreads<T>::value)
+template <typename T, int TPR, int NT, bool SCALED>
+__global__ void __launch_bounds__(NT)
 grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
                   const int* __restrict__ xlen, const int* __restrict__ ylen,
                   const typename Real<T>::pair* __restrict__ stat, const typename Lat<T>::val* __restrict__ alphas,
                   const typename Lat<T>::val* __restrict__ betas, const typename Lat<T>::val* __restrict__ llf, const T scale_in,
                   const T* __restrict__ scale_vec, const Dims d) {
     using R = Real<T>;
-    constexpr int NT = ChunkThreads<T>::value;
-    constexpr int ROWS = NT / TPR;
+    using Pair = typename R::pair;
+    constexpr int RPT = 1;   // rows per thread group (more was measured slower, see chunk_pass())
+    constexpr int RP = NT / TPR, ROWS = RP * RPT;
     extern __shared__ __align__(128) unsigned char chunk_raw[];
     T* tile = reinterpret_cast<T*>(chunk_raw);
     __shared__ __align__(8) unsigned long long bar_store;
@@ -193,35 +212,41 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
     const bool bulk = ((nelem * (uint32_t)sizeof(T)) & 15u) == 0;
     if (threadIdx.x == 0 && bulk) chunk_issue<T>(acts, tile, bar, r0, nrows, V);   // the copy goes out first
     T* gout = grads + (uint64_t)r0 * V;
+    pdl_wait();   // (PDL) the chunk was requested ahead of the lattice kernel's completion; its output is read below
 
     const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
-    const bool inrange = (uint32_t)i < nrows;
-    const uint32_t r = r0 + (inrange ? i : 0);
-    bool valid;
-    RowGrad<T> rg;
-    T scale = scale_in;
-    {
+    bool inrange[RPT], valid[RPT];
+    RowGrad<T> rg[RPT];
+    T scale[RPT];
+    bool any = false;
+#pragma unroll
+    for (int rp = 0; rp < RPT; ++rp) {
+        const uint32_t ri = rp * RP + i;
+        inrange[rp] = ri < nrows;
+        const uint32_t r = r0 + (inrange[rp] ? ri : 0);
+        scale[rp] = scale_in;
         uint32_t u, b, t;
         int Tb, Ub;
         d.decode(r, b, t, u);
         if constexpr (sizeof(T) == 4) {
             // every scalar of the row is requested in ONE round of loads, validity is sorted out afterwards
             // (addresses are in bounds for any t, u of the tensor: see the workspace slack in carve())
-            rg = row_grad_setup_spec(d, r, b, t, u, xlen, ylen, labels, stat, alphas, betas, llf, Tb, Ub);
-            if (SCALED && scale_vec) scale = __ldg(scale_vec + b) * scale_in;
-            valid = inrange && (int)t < Tb && (int)u < Ub;
+            rg[rp] = row_grad_setup_spec(d, r, b, t, u, xlen, ylen, labels, stat, alphas, betas, llf, Tb, Ub);
+            if (SCALED && scale_vec) scale[rp] = __ldg(scale_vec + b) * scale_in;
+            valid[rp] = inrange[rp] && (int)t < Tb && (int)u < Ub;
         } else {
             utt_extent(d, xlen, ylen, b, Tb, Ub);
-            valid = inrange && (int)t < Tb && (int)u < Ub;
-            rg.m = 0, rg.cA = 0, rg.cB = R::neg_inf(), rg.cL = R::neg_inf(), rg.y = -1;
-            if (valid) {
-                rg = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
-                if (SCALED && scale_vec) scale = __ldg(scale_vec + b) * scale_in;
+            valid[rp] = inrange[rp] && (int)t < Tb && (int)u < Ub;
+            rg[rp].m = 0, rg[rp].cA = 0, rg[rp].cB = R::neg_inf(), rg[rp].cL = R::neg_inf(), rg[rp].y = -1;
+            if (valid[rp]) {
+                rg[rp] = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
+                if (SCALED && scale_vec) scale[rp] = __ldg(scale_vec + b) * scale_in;
             }
         }
+        any = any || valid[rp];
     }
     // one barrier: publishes the mbarrier and tells whether any row of the chunk is a real cell
-    const bool any_valid = __syncthreads_or(valid);
+    const bool any_valid = __syncthreads_or(any);
     if (!any_valid) {   // the whole chunk is padding: zeros straight to global memory
         if (bulk) {
             constexpr int VEC = 16 / sizeof(T);
@@ -245,45 +270,49 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
 
     // Lanes sharing a row sit in one warp (TPR divides 32), so warp-level barriers order the reads of
     // the two special logits, the in-place sweep and the corrections.
-    T* x = tile + (inrange ? i : 0) * V;
-    T xb = 0, xy = 0;
-    if (valid) {
-        xb = x[d.blank];
-        xy = x[rg.y >= 0 ? rg.y : 0];
-    }
-    __syncwarp();
-    using Pair = typename R::pair;
-    Pair* x2 = reinterpret_cast<Pair*>(x);
-    if (valid) {
-        if ((V & 1) == 0) {   // pairs: one shared-memory load and one store per two elements
-#pragma unroll 4
-            for (int p = h; p < (V >> 1); p += TPR) {
-                Pair v = x2[p];
-                v.x = R::exp2(fma(v.x - rg.m, (T)R::kLog2e, rg.cA));
-                v.y = R::exp2(fma(v.y - rg.m, (T)R::kLog2e, rg.cA));
-                if (SCALED) v.x *= scale, v.y *= scale;
-                x2[p] = v;
-            }
-        } else {
-#pragma unroll 4
-            for (int k = h; k < V; k += TPR) {
-                T g = R::exp2(fma(x[k] - rg.m, (T)R::kLog2e, rg.cA));
-                if (SCALED) g *= scale;
-                x[k] = g;
-            }
+#pragma unroll
+    for (int rp = 0; rp < RPT; ++rp) {
+        const uint32_t ri = rp * RP + i;
+        T* x = tile + (size_t)(inrange[rp] ? ri : 0) * V;
+        const RowGrad<T>& g = rg[rp];
+        T xb = 0, xy = 0;
+        if (valid[rp]) {
+            xb = x[d.blank];
+            xy = x[g.y >= 0 ? g.y : 0];
         }
-    } else if (inrange) {
-        for (int k = h; k < V; k += TPR) x[k] = T(0);
-    }
-    __syncwarp();
-    if (valid && h == 0) {
-        T gb = R::exp2(fma(xb - rg.m, (T)R::kLog2e, rg.cB));
-        if (SCALED) gb *= scale;
-        x[d.blank] -= gb;
-        if (rg.y >= 0) {
-            T gl = R::exp2(fma(xy - rg.m, (T)R::kLog2e, rg.cL));
-            if (SCALED) gl *= scale;
-            x[rg.y] -= gl;
+        __syncwarp();
+        Pair* x2 = reinterpret_cast<Pair*>(x);
+        if (valid[rp]) {
+            if ((V & 1) == 0) {   // pairs: one shared-memory load and one store per two elements
+#pragma unroll 4
+                for (int p = h; p < (V >> 1); p += TPR) {
+                    Pair v = x2[p];
+                    v.x = R::exp2(fma(v.x - g.m, (T)R::kLog2e, g.cA));
+                    v.y = R::exp2(fma(v.y - g.m, (T)R::kLog2e, g.cA));
+                    if (SCALED) v.x *= scale[rp], v.y *= scale[rp];
+                    x2[p] = v;
+                }
+            } else {
+#pragma unroll 4
+                for (int k = h; k < V; k += TPR) {
+                    T e = R::exp2(fma(x[k] - g.m, (T)R::kLog2e, g.cA));
+                    if (SCALED) e *= scale[rp];
+                    x[k] = e;
+                }
+            }
+        } else if (inrange[rp]) {
+            for (int k = h; k < V; k += TPR) x[k] = T(0);
+        }
+        __syncwarp();
+        if (valid[rp] && h == 0) {
+            T gb = R::exp2(fma(xb - g.m, (T)R::kLog2e, g.cB));
+            if (SCALED) gb *= scale[rp];
+            x[d.blank] -= gb;
+            if (g.y >= 0) {
+                T gl = R::exp2(fma(xy - g.m, (T)R::kLog2e, g.cL));
+                if (SCALED) gl *= scale[rp];
+                x[g.y] -= gl;
+            }
         }
     }
     if (bulk) {

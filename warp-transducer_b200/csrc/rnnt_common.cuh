@@ -262,6 +262,12 @@ __device__ __forceinline__ LogVal to_logval(float v, int e) {
 }
 
 
+// Programmatic dependent launch (PDL).  pdl_trigger(): this CTA no longer holds back the launch of the
+// next kernel in the stream; pdl_wait(): everything the previous kernel wrote is complete and visible.
+// Both are no-ops for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Per-type lattice storage: what pass 1 writes per cell (`fac`) and what the wavefront stores (`val`).

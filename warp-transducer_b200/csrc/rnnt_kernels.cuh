@@ -83,6 +83,7 @@ rowstats_row_kernel(const IO* __restrict__ acts, const int* __restrict__ labels,
     using R = Real<T>;
     constexpr int kRowThreads = RowThreads<IO>::value;
     __shared__ T sh_m[kRowThreads / 32], sh_s[kRowThreads / 32];
+    pdl_trigger();   // the lattice kernel may be launched as soon as every CTA of this grid has started
     const uint32_t r = blockIdx.x;
     uint32_t u, b, t;
     d.decode(r, b, t, u);
@@ -176,6 +177,7 @@ rowstats_tile_kernel(const IO* __restrict__ acts, const int* __restrict__ labels
     const int sub = lane / LPR, sl = lane % LPR;
     const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nv = d.V / VEC;
+    pdl_trigger();
 
     {   // non-persistent: one tile of RPW rows per warp (see rowstats_row_kernel for why)
         const uint64_t r0 = gw * RPW;
@@ -300,6 +302,8 @@ lattice_kernel(const typename Real<T>::pair* __restrict__ lp2, const int* __rest
     const int nwarps = NT >> 5;
     int Tb, Ub;
     utt_extent(d, xlen, ylen, b, Tb, Ub);
+    pdl_trigger();
+    pdl_wait();   // pass 1's factors are complete
     const size_t base = (size_t)b * lattice_block(d);
     const int last = Tb + Ub - 2;
     const int mU = d.maxU;
@@ -588,6 +592,7 @@ grad_row_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int* 
         }
     };
     load(threadIdx.x);  // in flight before the lattice constants are fetched
+    pdl_wait();         // (PDL) the logits were read ahead of the lattice kernel's completion; its output is not
     const RowGrad<T> rg = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
     auto emit = [&](int base) {
 #pragma unroll
@@ -649,6 +654,7 @@ grad_tile_kernel(const IO* __restrict__ acts, IO* __restrict__ grads, const int*
             const int i = sl + j * LPR;
             if (i < nv) x[j] = ld_stream<T, VEC>(row + (size_t)i * VEC);
         }
+        pdl_wait();
         const RowGrad<T> rg = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
 #pragma unroll
         for (int j = 0; j < kVPL; ++j) {

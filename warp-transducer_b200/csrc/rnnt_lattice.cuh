@@ -271,6 +271,8 @@ lattice_lin_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen,
         __syncthreads();
     }
     const uint32_t ring_base = smem_u32(ring_raw), edge_base = smem_u32(edge), prog_base = smem_u32(prog);
+    pdl_trigger();   // the gradient kernel may launch and read the logits while the wavefront runs
+    pdl_wait();      // pass 1's factors are complete and visible
     if (blockIdx.y == 0)
         lattice_lin_body<MULTI, false>(fac, xlen, ylen, alphas, llf, costs, d, ring_base, edge_base, prog_base, &bad_any);
     else
