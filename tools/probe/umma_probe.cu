@@ -71,5 +71,8 @@ int main() {
     run_case<false, false, 32, 32, 2, 2>("S  two stages", 2, 150, 21, 60, 1);
     run_case<true, false, 192, 24>("dF N=192", 2, 200, 150, 21, 1);
     run_case<true, false, 256, 24>("dF N=256 tiled", 1, 200, 300, 40, 1);
+    run_case<true, false, 64, 24, 3, 1>("dF float4 transposing fetch", 2, 200, 150, 21, 1);
+    run_case<true, true, 32, 24, 3, 0>("dG float4 transposing fetch", 2, 200, 21, 150, 1);
+    run_case<true, false, 192, 24, 3, 1>("dF N=192 float4 transposing", 2, 328, 150, 21, 1);
     return 0;
 }

@@ -76,8 +76,13 @@ __device__ __forceinline__ void chunk_issue(const T* __restrict__ acts, T* tile,
 
 // =================================================================================================
 // Pass 1 on a chunk: per row (max, log sum exp) and the lattice's transition factors.
-// The CTA size NT is a template parameter: a chunk CTA is one latency chain (copy -> scalars -> walk ->
-// stores), so for very short rows more, smaller CTAs per SM keep more chains in flight.
+//
+// Per-row SCALAR work (index decoding, lengths, label, the statistics' logarithm, the factor split, the
+// skewed store address) is done ROW-PARALLEL: thread r of the CTA owns row r's scalars, so that work runs
+// on ROWS/32 fully populated warps instead of being repeated by (or idling) the TPR lanes that share a row.
+// At V=28 it was most of the kernel (ncu: 54 instructions per element, 87 % issue-active).
+// The element walk is group-parallel: TPR lanes per row, results handed over through shared memory.
+// The CTA size NT is a template parameter (tuning hook; 256 measured best on B200).
 // =================================================================================================
 template <typename T, int TPR, int NT>
 __global__ void __launch_bounds__(NT)
@@ -86,11 +91,11 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
                       typename Lat<T>::fac* __restrict__ lp2, const Dims d) {
     using R = Real<T>;
     using Pair = typename R::pair;
-    constexpr int RPT = 1;   // rows per thread group (more was measured slower, see chunk_pass())
-    constexpr int RP = NT / TPR, ROWS = RP * RPT;
+    constexpr int ROWS = NT / TPR;
     extern __shared__ __align__(128) unsigned char chunk_raw[];
     T* tile = reinterpret_cast<T*>(chunk_raw);
     __shared__ __align__(8) unsigned long long bar_store;
+    __shared__ Pair row_ms[ROWS];   // (max, sum of exponentials) per row, group leaders -> row owners
     const uint32_t bar = smem_u32(&bar_store);
     const uint32_t r0 = blockIdx.x * ROWS;
     const uint32_t nrows = min((uint32_t)ROWS, d.rows - r0);
@@ -100,29 +105,22 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
     if (threadIdx.x == 0 && bulk) chunk_issue<T>(acts, tile, bar, r0, nrows, V);
     pdl_trigger();
 
-    // per-row bookkeeping while the copy is in flight (all rows of this thread group up front)
-    const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
-    bool valid[RPT];
-    int y[RPT];
-    bool any = false;
-#pragma unroll
-    for (int rp = 0; rp < RPT; ++rp) {
-        const uint32_t ri = rp * RP + i;
-        valid[rp] = ri < nrows;
-        y[rp] = -1;
-        if (valid[rp]) {
-            uint32_t u, b, t;
-            int Tb, Ub;
-            d.decode(r0 + ri, b, t, u);
-            utt_extent(d, xlen, ylen, b, Tb, Ub);
-            valid[rp] = (int)t < Tb && (int)u < Ub;
-            if (valid[rp] && h == 0 && (int)u < Ub - 1) y[rp] = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
-        }
-        any = any || valid[rp];
+    // row-parallel bookkeeping while the copy is in flight: thread r <-> row r0 + r
+    bool valid = threadIdx.x < nrows;
+    int y = -1;
+    size_t q = 0;
+    if (valid) {
+        uint32_t u, b, t;
+        int Tb, Ub;
+        d.decode(r0 + threadIdx.x, b, t, u);
+        utt_extent(d, xlen, ylen, b, Tb, Ub);
+        valid = (int)t < Tb && (int)u < Ub;
+        if (valid && (int)u < Ub - 1) y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
+        q = skew(d, b, t, u);
     }
     // one barrier: publishes the mbarrier to the waiters and tells whether any row of the chunk is a
     // real cell (a fully padded chunk - ragged batches only - costs one wasted read, nothing else)
-    const bool any_valid = __syncthreads_or(any);
+    const bool any_valid = __syncthreads_or(valid);
     if (!any_valid) {
         if (bulk && threadIdx.x == 0) mbar_wait(bar, 0);   // shared memory must outlive the in-flight copy
         return;
@@ -135,14 +133,13 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
         __syncthreads();
     }
 
-    // Even V: a row is walked as PAIRS (one 8/16-byte shared-memory access per two elements) - half the
-    // load instructions of an issue-bound kernel; the row start is pair-aligned because V is even.
-    const bool paired = (V & 1) == 0;
-#pragma unroll
-    for (int rp = 0; rp < RPT; ++rp) {
-        const uint32_t ri = rp * RP + i;
-        const T* x = tile + (size_t)(valid[rp] ? ri : 0) * V;   // rows that are not valid walk row 0 (results discarded)
+    // group-parallel walk.  Even V: a row is walked as PAIRS (one 8/16-byte shared-memory access per two
+    // elements); the row start is pair-aligned because V is even.  Rows past the chunk walk row 0.
+    {
+        const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
+        const T* x = tile + (size_t)((uint32_t)i < nrows ? i : 0) * V;
         const Pair* x2 = reinterpret_cast<const Pair*>(x);
+        const bool paired = (V & 1) == 0;
         T m = R::neg_inf();
         if (paired) {
 #pragma unroll 4
@@ -156,38 +153,55 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
         }
         const T M = group_max<TPR>(m);
         const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
-        T s = 0;
+        T sum = 0;
         if (paired) {
 #pragma unroll 4
             for (int p = h; p < (V >> 1); p += TPR) {
                 const Pair v = x2[p];
-                s += es.term(v.x) + es.term(v.y);
+                sum += es.term(v.x) + es.term(v.y);
             }
         } else {
 #pragma unroll 4
-            for (int k = h; k < V; k += TPR) s += es.term(x[k]);
+            for (int k = h; k < V; k += TPR) sum += es.term(x[k]);
         }
-        const T S = group_sum<TPR>(s);
-        if (valid[rp] && h == 0) {
-            const T lse = es.log_of(S);
-            Pair st;
-            st.x = M;
-            st.y = lse;
-            const uint32_t r = r0 + ri;
-            stat[r] = st;
-            uint32_t u, b, t;
-            d.decode(r, b, t, u);
-            lp2[skew(d, b, t, u)] =
-                Lat<T>::make((x[d.blank] - M) - lse, y[rp] >= 0 ? (x[y[rp]] - M) - lse : T(0), y[rp] >= 0);
+        const T S = group_sum<TPR>(sum);
+        if (h == 0) {
+            Pair ms;
+            ms.x = M;
+            ms.y = S;
+            row_ms[i] = ms;
         }
+    }
+    __syncthreads();
+    // row-parallel epilogue: thread r finishes row r
+    if (valid) {
+        const Pair ms = row_ms[threadIdx.x];
+        const T M = ms.x;
+        const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
+        const T lse = es.log_of(ms.y);
+        const T* x = tile + (size_t)threadIdx.x * V;
+        Pair st;
+        st.x = M;
+        st.y = lse;
+        stat[r0 + threadIdx.x] = st;
+        lp2[q] = Lat<T>::make((x[d.blank] - M) - lse, y >= 0 ? (x[y] - M) - lse : T(0), y >= 0);
     }
 }
 
 // =================================================================================================
 // Pass 2 on a chunk: gradient in place in shared memory, one bulk store.  Formula and per-row
 // constants as grad_row_kernel (rnnt_kernels.cuh); the blank / label corrections are applied to the
-// two affected words of the row after the sweep.
+// two affected words of the row after the sweep.  The per-row constants are fetched row-parallel (thread r
+// <-> row r: one round of loads for the whole chunk) and handed to the row's lanes through shared memory.
 // =================================================================================================
+template <typename T> struct __align__(16) ChunkRow {
+    T m, cA, cB, cL;
+    T scale;
+    int y;
+    int valid;
+    int pad;
+};
+
 template <typename T, int TPR, int NT, bool SCALED>
 __global__ void __launch_bounds__(NT)
 grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* __restrict__ labels,
@@ -197,11 +211,11 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
                   const T* __restrict__ scale_vec, const Dims d) {
     using R = Real<T>;
     using Pair = typename R::pair;
-    constexpr int RPT = 1;   // rows per thread group (more was measured slower, see chunk_pass())
-    constexpr int RP = NT / TPR, ROWS = RP * RPT;
+    constexpr int ROWS = NT / TPR;
     extern __shared__ __align__(128) unsigned char chunk_raw[];
     T* tile = reinterpret_cast<T*>(chunk_raw);
     __shared__ __align__(8) unsigned long long bar_store;
+    __shared__ ChunkRow<T> rowc[1];   // (ROWS entries if ROWPAR is switched on)
     const uint32_t bar = smem_u32(&bar_store);
     // chunks in reverse order: the tail of pass 1 is met first in L2
     const uint32_t nchunks = gridDim.x;
@@ -214,39 +228,57 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
     T* gout = grads + (uint64_t)r0 * V;
     pdl_wait();   // (PDL) the chunk was requested ahead of the lattice kernel's completion; its output is read below
 
-    const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
-    bool inrange[RPT], valid[RPT];
-    RowGrad<T> rg[RPT];
-    T scale[RPT];
-    bool any = false;
-#pragma unroll
-    for (int rp = 0; rp < RPT; ++rp) {
-        const uint32_t ri = rp * RP + i;
-        inrange[rp] = ri < nrows;
-        const uint32_t r = r0 + (inrange[rp] ? ri : 0);
-        scale[rp] = scale_in;
+    // Row constants: every lane fetches its row's constants itself (lanes of a row hit the same addresses, so
+    // the loads coalesce into one request per row).  The row-parallel form (thread r <-> row r, hand-over
+    // through shared memory, as in pass 1) is kept behind ROWPAR: measured on B200 it is slower here - at
+    // V=28 the extra shared-memory hop behind the barrier costs more than the saved instructions (grad
+    // 43 -> 47 us), and at V=50 the hand-over array costs the eighth resident CTA per SM.
+    constexpr bool ROWPAR = false;
+    auto fetch = [&](uint32_t row_in_chunk) {
+        const bool inrange = row_in_chunk < nrows;
+        const uint32_t r = r0 + (inrange ? row_in_chunk : 0);
+        ChunkRow<T> c;
+        c.scale = scale_in;
         uint32_t u, b, t;
         int Tb, Ub;
         d.decode(r, b, t, u);
+        RowGrad<T> rg;
+        bool v;
         if constexpr (sizeof(T) == 4) {
             // every scalar of the row is requested in ONE round of loads, validity is sorted out afterwards
             // (addresses are in bounds for any t, u of the tensor: see the workspace slack in carve())
-            rg[rp] = row_grad_setup_spec(d, r, b, t, u, xlen, ylen, labels, stat, alphas, betas, llf, Tb, Ub);
-            if (SCALED && scale_vec) scale[rp] = __ldg(scale_vec + b) * scale_in;
-            valid[rp] = inrange[rp] && (int)t < Tb && (int)u < Ub;
+            rg = row_grad_setup_spec(d, r, b, t, u, xlen, ylen, labels, stat, alphas, betas, llf, Tb, Ub);
+            if (SCALED && scale_vec) c.scale = __ldg(scale_vec + b) * scale_in;
+            v = inrange && (int)t < Tb && (int)u < Ub;
         } else {
             utt_extent(d, xlen, ylen, b, Tb, Ub);
-            valid[rp] = inrange[rp] && (int)t < Tb && (int)u < Ub;
-            rg[rp].m = 0, rg[rp].cA = 0, rg[rp].cB = R::neg_inf(), rg[rp].cL = R::neg_inf(), rg[rp].y = -1;
-            if (valid[rp]) {
-                rg[rp] = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
-                if (SCALED && scale_vec) scale[rp] = __ldg(scale_vec + b) * scale_in;
+            v = inrange && (int)t < Tb && (int)u < Ub;
+            rg.m = 0, rg.cA = 0, rg.cB = R::neg_inf(), rg.cL = R::neg_inf(), rg.y = -1;
+            if (v) {
+                rg = row_grad_setup(d, r, b, t, u, Tb, Ub, labels, stat, alphas, betas, llf);
+                if (SCALED && scale_vec) c.scale = __ldg(scale_vec + b) * scale_in;
             }
         }
-        any = any || valid[rp];
+        c.m = rg.m, c.cA = rg.cA, c.cB = rg.cB, c.cL = rg.cL, c.y = rg.y;
+        c.valid = v ? 1 : (inrange ? 0 : -1);   // -1: row does not exist (past the end of the tensor)
+        c.pad = 0;
+        return c;
+    };
+    bool valid = false;
+    ChunkRow<T> g;
+    if constexpr (ROWPAR) {
+        static_assert(!ROWPAR, "size rowc[ROWS] before enabling");
+        if (threadIdx.x < ROWS) {
+            const ChunkRow<T> c = fetch(threadIdx.x);
+            valid = c.valid > 0;
+            rowc[threadIdx.x] = c;
+        }
+    } else {
+        g = fetch(threadIdx.x / TPR);
+        valid = g.valid > 0;
     }
-    // one barrier: publishes the mbarrier and tells whether any row of the chunk is a real cell
-    const bool any_valid = __syncthreads_or(any);
+    // one barrier: publishes the mbarrier and the row constants, and tells whether any row is a real cell
+    const bool any_valid = __syncthreads_or(valid);
     if (!any_valid) {   // the whole chunk is padding: zeros straight to global memory
         if (bulk) {
             constexpr int VEC = 16 / sizeof(T);
@@ -270,49 +302,47 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
 
     // Lanes sharing a row sit in one warp (TPR divides 32), so warp-level barriers order the reads of
     // the two special logits, the in-place sweep and the corrections.
-#pragma unroll
-    for (int rp = 0; rp < RPT; ++rp) {
-        const uint32_t ri = rp * RP + i;
-        T* x = tile + (size_t)(inrange[rp] ? ri : 0) * V;
-        const RowGrad<T>& g = rg[rp];
-        T xb = 0, xy = 0;
-        if (valid[rp]) {
-            xb = x[d.blank];
-            xy = x[g.y >= 0 ? g.y : 0];
-        }
-        __syncwarp();
-        Pair* x2 = reinterpret_cast<Pair*>(x);
-        if (valid[rp]) {
-            if ((V & 1) == 0) {   // pairs: one shared-memory load and one store per two elements
+    const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
+    if constexpr (ROWPAR) g = rowc[i];
+    const bool rvalid = g.valid > 0, inrange = g.valid >= 0;
+    T* x = tile + (size_t)(inrange ? i : 0) * V;
+    T xb = 0, xy = 0;
+    if (rvalid) {
+        xb = x[d.blank];
+        xy = x[g.y >= 0 ? g.y : 0];
+    }
+    __syncwarp();
+    Pair* x2 = reinterpret_cast<Pair*>(x);
+    if (rvalid) {
+        if ((V & 1) == 0) {   // pairs: one shared-memory load and one store per two elements
 #pragma unroll 4
-                for (int p = h; p < (V >> 1); p += TPR) {
-                    Pair v = x2[p];
-                    v.x = R::exp2(fma(v.x - g.m, (T)R::kLog2e, g.cA));
-                    v.y = R::exp2(fma(v.y - g.m, (T)R::kLog2e, g.cA));
-                    if (SCALED) v.x *= scale[rp], v.y *= scale[rp];
-                    x2[p] = v;
-                }
-            } else {
+            for (int p = h; p < (V >> 1); p += TPR) {
+                Pair v = x2[p];
+                v.x = R::exp2(fma(v.x - g.m, (T)R::kLog2e, g.cA));
+                v.y = R::exp2(fma(v.y - g.m, (T)R::kLog2e, g.cA));
+                if (SCALED) v.x *= g.scale, v.y *= g.scale;
+                x2[p] = v;
+            }
+        } else {
 #pragma unroll 4
-                for (int k = h; k < V; k += TPR) {
-                    T e = R::exp2(fma(x[k] - g.m, (T)R::kLog2e, g.cA));
-                    if (SCALED) e *= scale[rp];
-                    x[k] = e;
-                }
+            for (int k = h; k < V; k += TPR) {
+                T e = R::exp2(fma(x[k] - g.m, (T)R::kLog2e, g.cA));
+                if (SCALED) e *= g.scale;
+                x[k] = e;
             }
-        } else if (inrange[rp]) {
-            for (int k = h; k < V; k += TPR) x[k] = T(0);
         }
-        __syncwarp();
-        if (valid[rp] && h == 0) {
-            T gb = R::exp2(fma(xb - g.m, (T)R::kLog2e, g.cB));
-            if (SCALED) gb *= scale[rp];
-            x[d.blank] -= gb;
-            if (g.y >= 0) {
-                T gl = R::exp2(fma(xy - g.m, (T)R::kLog2e, g.cL));
-                if (SCALED) gl *= scale[rp];
-                x[g.y] -= gl;
-            }
+    } else if (inrange) {
+        for (int k = h; k < V; k += TPR) x[k] = T(0);
+    }
+    __syncwarp();
+    if (rvalid && h == 0) {
+        T gb = R::exp2(fma(xb - g.m, (T)R::kLog2e, g.cB));
+        if (SCALED) gb *= g.scale;
+        x[d.blank] -= gb;
+        if (g.y >= 0) {
+            T gl = R::exp2(fma(xy - g.m, (T)R::kLog2e, g.cL));
+            if (SCALED) gl *= g.scale;
+            x[g.y] -= gl;
         }
     }
     if (bulk) {

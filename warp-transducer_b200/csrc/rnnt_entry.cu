@@ -109,10 +109,14 @@ struct SidePool {
     bool ok = false;
 };
 SidePool& side_pool() {
-    thread_local SidePool pool;
+    // one pool per (host thread, device): a thread that alternates devices finds its pools again instead
+    // of re-creating (and leaking) streams and events on every switch
+    constexpr int kMaxDevices = 64;
+    thread_local SidePool pools[kMaxDevices];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (pool.device != dev) {  // first use on this thread/device (pools of other devices are leaked, tiny)
+    SidePool& pool = pools[dev >= 0 && dev < kMaxDevices ? dev : 0];
+    if (pool.device != dev) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         pool.ok = true;
@@ -575,6 +579,7 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         }
     } else {
         SidePool& pool = side_pool();
+        bool fork_ok = true;   // a failed fork/join would leave the gradient pass unordered against a lattice
         Group gs[kMaxGroups];
         for (int k = 0; k < groups; ++k) {
             const int b0 = (int)((int64_t)N * k / groups), b1 = (int)((int64_t)N * (k + 1) / groups);
@@ -584,21 +589,25 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         for (int k = 0; k < groups; ++k) {
             stream_pass<T, IO>(gs[k].acts, nullptr, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w, scale,
                                gs[k].scale_vec, gs[k].d, s, 1);
-            cudaEventRecord(pool.forked[k], s);
-            cudaStreamWaitEvent(pool.stream[k], pool.forked[k], 0);
+            fork_ok &= cudaEventRecord(pool.forked[k], s) == cudaSuccess;
+            fork_ok &= cudaStreamWaitEvent(pool.stream[k], pool.forked[k], 0) == cudaSuccess;
             launch_lattice(gs[k], pool.stream[k]);
-            cudaEventRecord(pool.joined[k], pool.stream[k]);
+            fork_ok &= cudaEventRecord(pool.joined[k], pool.stream[k]) == cudaSuccess;
         }
         mark(1, s);
         // main stream: join each lattice, then that group's pass 2 (or just join, forward-only)
         for (int k = 0; k < groups; ++k) {
-            cudaStreamWaitEvent(s, pool.joined[k], 0);
+            fork_ok &= cudaStreamWaitEvent(s, pool.joined[k], 0) == cudaSuccess;
             if (k == 0) mark(2, s);
             if (grads && phase != kForward)
                 stream_pass<T, IO>(gs[k].acts, gs[k].grads, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w,
                                    scale, gs[k].scale_vec, gs[k].d, s, 2);
         }
         if (grads && phase != kForward) mark(3, s);
+        if (!fork_ok) {
+            cudaStreamSynchronize(s);
+            return RNNT_STATUS_EXECUTION_FAILED;
+        }
     }
 
     g_pdl = false;
@@ -771,10 +780,13 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
             umma::Operand WmUT{w.wm, (long long)T * U, 1, U, U};   // (n = u, k = t): n-contiguous
             // 64-column accumulator tiles: small tensor-memory / shared-memory footprint -> several CTAs per SM,
             // and the whole tile's Ef fetches are in flight before the accumulator is read
-            launch_umma<0, 1, 24>(EgT, WmTU, V, T, U, 1, N,
-                                  umma::Epilogue{w.ef, (long long)T * V, 1, V, dF, 0, (long long)T * V, 1, V}, s, 64);
-            launch_umma<0, 0, 24>(EfT, WmUT, V, U, T, 1, N,
-                                  umma::Epilogue{w.eg, (long long)U * V, 1, V, dG, 0, (long long)U * V, 1, V}, s);
+            static const int df_tile = [] { const char* e = getenv("RNNT_B200_DF_TILE"); return e ? atoi(e) : 64; }();
+            const umma::Epilogue epf{w.ef, (long long)T * V, 1, V, dF, 0, (long long)T * V, 1, V};
+            if (V % 4 == 0) launch_umma<3, 1, 24>(EgT, WmTU, V, T, U, 1, N, epf, s, df_tile);   // 16-byte aligned rows
+            else launch_umma<0, 1, 24>(EgT, WmTU, V, T, U, 1, N, epf, s, df_tile);
+            const umma::Epilogue epg{w.eg, (long long)U * V, 1, V, dG, 0, (long long)U * V, 1, V};
+            if (V % 4 == 0) launch_umma<3, 0, 24>(EfT, WmUT, V, U, T, 1, N, epg, s);
+            else launch_umma<0, 0, 24>(EfT, WmUT, V, U, T, 1, N, epg, s);
         } else if (V >= 512) {  // long vocabulary: one thread per column, thin contraction
             {   // dF[t,v] = Ef[t,v] * sum_u Wm[t,u] Eg[u,v]
                 dim3 grid((V + 255) / 256, (T + kJointRT - 1) / kJointRT, N);

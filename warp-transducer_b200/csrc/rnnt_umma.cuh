@@ -138,6 +138,12 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 //  MODE 1 (k-contiguous, unaligned rows, KS <= 32): scalar; lane = k, warp = row.
 //  MODE 0 (mn-contiguous): scalar; a warp covers 8 consecutive mn x 4 consecutive k - four full 32-byte
 //         sectors per load instruction, 32 different banks per store (the transposition happens here).
+//  MODE 3 (mn-contiguous, 16-byte aligned rows): float4 loads of 4 consecutive mn at one k; a warp covers
+//         16 mn x 8 k (eight 64-byte row pieces per load instruction); the four values go to four
+//         consecutive 16-byte chunks of the K-major layout (immediate offsets), bank-conflict free at KS=24.
+// Rows beyond mn_valid are neither loaded nor stored: a row of D depends on its own row of A only (and a
+// column on its own row of B), and the epilogue never reads those rows/columns - so M tiles with few real
+// rows (T=150: the second tile has 22) cost what their real rows cost.  The k padding IS zero-filled.
 constexpr int kThreads = 256;   // 8 warps: two per accumulator lane quarter (they split the columns in the epilogue)
 template <int MODE, int MN, int KS> struct StageRegs {
     static constexpr int CH = KS / 4;                 // 16-byte chunks per row
@@ -145,13 +151,20 @@ template <int MODE, int MN, int KS> struct StageRegs {
     static constexpr int MB = MN / 8;                 // MODE 0: 8-row blocks per k-group
     static constexpr int Q = MB >= 8 ? MB / 8 : 1;    // MODE 0, MB >= 8: passes over mn per k-group
     static constexpr int KB_STEP = MB >= 8 ? 1 : 8 / MB;   // MODE 0: k-groups advanced per pass (MB < 8: several at once)
-    static constexpr int PER = MODE == 2 ? (MN + RP - 1) / RP : MODE == 1 ? MN / 8 : MB >= 8 ? Q * CH : (CH + KB_STEP - 1) / KB_STEP;
+    static constexpr int MT = MN / 16 > 0 ? MN / 16 : 1;   // MODE 3: 16-row tiles along mn
+    static constexpr int KT = KS / 8;                     // MODE 3: 8-wide tiles along k
+    static constexpr int PER = MODE == 2   ? (MN + RP - 1) / RP
+                               : MODE == 1 ? MN / 8
+                               : MODE == 3 ? (MT * KT + 7) / 8
+                               : MB >= 8   ? Q * CH
+                                           : (CH + KB_STEP - 1) / KB_STEP;
+    static_assert(MODE != 3 || (MN % 16 == 0 && (MT >= 8 ? MT % 8 == 0 : 8 % MT == 0)), "MODE 3 needs MN in {16..128} or a multiple of 128");
     static_assert(MODE != 2 || (kThreads % CH == 0 && RP % 8 == 0), "MODE 2 needs KS in {8,16,32,64}");
     static_assert(MODE != 1 || KS <= 32, "MODE 1 needs KS <= 32");
     static_assert(MODE != 0 || (MB >= 8 ? MB % 8 == 0 : 8 % MB == 0), "MODE 0 needs MN in {8,16,32,64} or a multiple of 64");
 
-    float4 v4[MODE == 2 ? PER : 1];
-    float v1[MODE == 2 ? 1 : PER];
+    float4 v4[(MODE == 2 || MODE == 3) ? PER : 1];
+    float v1[(MODE == 2 || MODE == 3) ? 1 : PER];
     const float* g0;      // this thread's element 0 at k0 = 0
     long long g_mn, g_k;  // global strides (elements) along mn / k
     uint32_t o0;          // shared-memory offset of element 0
@@ -166,6 +179,10 @@ template <int MODE, int MN, int KS> struct StageRegs {
         } else if (MODE == 1) {
             mn_first = w;
             k_first = lane;
+        } else if (MODE == 3) {
+            // warp tile = 16 mn x 8 k; tile index of pass j: w + 8j -> (mt, kt) = (ti % MT, ti / MT)
+            mn_first = (MT >= 8 ? w : w % MT) * 16 + (tid & 3) * 4;
+            k_first = (MT >= 8 ? 0 : w / MT) * 8 + ((tid >> 2) & 7);
         } else {
             const int mm = tid & 7, kk = (tid >> 3) & 3;
             mn_first = (MB >= 8 ? w : w % MB) * 8 + mm;
@@ -177,10 +194,14 @@ template <int MODE, int MN, int KS> struct StageRegs {
     }
     // (mn step, k step) of element j relative to element 0 - compile-time
     static __device__ __forceinline__ constexpr int dmn(int j) {
-        return MODE == 2 ? j * RP : MODE == 1 ? 8 * j : MB >= 8 ? 64 * (j % Q) : 0;
+        return MODE == 2 ? j * RP : MODE == 1 ? 8 * j : MODE == 3 ? (MT >= 8 ? 128 * (j % (MT / 8)) : 0)
+                                                      : MB >= 8   ? 64 * (j % Q)
+                                                                  : 0;
     }
     static __device__ __forceinline__ constexpr int dk(int j) {
-        return MODE == 2 ? 0 : MODE == 1 ? 0 : MB >= 8 ? 4 * (j / Q) : 4 * KB_STEP * j;
+        return MODE == 2 ? 0 : MODE == 1 ? 0 : MODE == 3 ? (MT >= 8 ? 8 * (j / (MT / 8)) : 8 * (8 / MT) * j)
+                                                      : MB >= 8   ? 4 * (j / Q)
+                                                                  : 4 * KB_STEP * j;
     }
     __device__ __forceinline__ void load(int k0, int k_end) {
         const float* g = g0 + (long long)k0 * g_k;
@@ -190,7 +211,18 @@ template <int MODE, int MN, int KS> struct StageRegs {
             const bool in = dmn(j) < mn_lim && kj < k_end && (MODE != 1 || k_first < KS) &&
                             (MODE == 2 ? mn_first + dmn(j) < MN : k_first + dk(j) < KS);
             const float* p = g + (long long)dmn(j) * g_mn + (long long)dk(j) * g_k;
-            if (MODE == 2) {
+            if (MODE == 3) {
+                v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (in) {
+                    if (dmn(j) + 3 < mn_lim) {
+                        v4[j] = __ldg(reinterpret_cast<const float4*>(p));
+                    } else {   // ragged end of the mn range
+                        v4[j].x = __ldg(p);
+                        if (dmn(j) + 1 < mn_lim) v4[j].y = __ldg(p + 1);
+                        if (dmn(j) + 2 < mn_lim) v4[j].z = __ldg(p + 2);
+                    }
+                }
+            } else if (MODE == 2) {
                 v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (in) {
                     if (kj + 3 < k_end) {
@@ -211,9 +243,20 @@ template <int MODE, int MN, int KS> struct StageRegs {
         for (int j = 0; j < PER; ++j) {
             // offset step of element j: row groups are SBO apart, k-chunks kPad apart (compile-time)
             const uint32_t o = o0 + (uint32_t)(dmn(j) / 8) * TileGeom::sbo(KS) + (uint32_t)(dk(j) / 4) * kPad;
-            const bool slot = (MODE == 2 ? mn_first + dmn(j) < MN : k_first + dk(j) < KS) && (MODE != 1 || k_first < KS);
+            // rows past mn_valid are skipped (see above); the k padding of real rows is written as zeros
+            const bool slot = (MODE == 2 ? mn_first + dmn(j) < MN : k_first + dk(j) < KS) && (MODE != 1 || k_first < KS) &&
+                              dmn(j) < mn_lim;
             if (slot) {
-                if (MODE == 2) {
+                if (MODE == 3) {
+                    const float xs[4] = {v4[j].x, v4[j].y, v4[j].z, v4[j].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {   // mn + c sits one 16-byte chunk further (same 8-row group)
+                        float h, l;
+                        split_tf32(xs[c], h, l);
+                        *reinterpret_cast<float*>(hi + o + 16 * c) = h;
+                        *reinterpret_cast<float*>(lo + o + 16 * c) = l;
+                    }
+                } else if (MODE == 2) {
                     float4 h, l;
                     split_tf32(v4[j].x, h.x, l.x);
                     split_tf32(v4[j].y, h.y, l.y);
