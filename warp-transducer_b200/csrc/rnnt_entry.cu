@@ -514,7 +514,13 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
                          static_cast<LogVal*>(g.w.alphas), static_cast<LogVal*>(g.w.betas), static_cast<LogVal*>(g.w.llf),
                          static_cast<LogVal*>(g.w.llb), g.costs, g.d);
             };
-            if (threads > 32) launch(lattice_lin_kernel<true>, kLinStaticSmem);
+            static const bool two_col = [] { const char* e = getenv("RNNT_B200_LATTICE2"); return !(e && atoi(e) == 0); }();
+            if (threads > 32 && opt.maxU <= 64 && two_col) {
+                // 33..64 labels: one warp per direction, two columns per lane, no cross-warp exchange
+                launch_k(lattice_lin2_kernel, grid, dim3(32), 0, st, g_pdl, static_cast<const float4*>(g.w.lp2), g.xlen,
+                         g.ylen, static_cast<LogVal*>(g.w.alphas), static_cast<LogVal*>(g.w.betas),
+                         static_cast<LogVal*>(g.w.llf), static_cast<LogVal*>(g.w.llb), g.costs, g.d);
+            } else if (threads > 32) launch(lattice_lin_kernel<true>, kLinStaticSmem);
             else launch(lattice_lin_kernel<false>, 64);
         } else {
             // fp64: log-domain wavefront (rnnt_kernels.cuh)

@@ -254,6 +254,138 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
     }
 }
 
+// =================================================================================================
+// 32 < maxU <= 64: ONE warp per direction, TWO adjacent columns per lane (u0 = 2*lane, u1 = u0 + 1).
+// The neighbour of the second column is the lane's own first column (a register), only the first
+// column's neighbour crosses lanes - one shuffle pair per step serves two cells, the two cell updates are
+// independent (ILP 2), and there is no cross-warp exchange at all.  Same arithmetic, ring and neutral-
+// factor conventions as lattice_lin_body.
+// =================================================================================================
+template <bool BACKWARD>
+__device__ __forceinline__ void lattice_lin_body2(const float4* __restrict__ fac, const int* __restrict__ xlen,
+                                                  const int* __restrict__ ylen, LogVal* __restrict__ out,
+                                                  LogVal* __restrict__ llout, float* __restrict__ costs,
+                                                  const Dims& d, uint32_t ring_base) {
+    constexpr int DIR = BACKWARD ? -1 : 1;
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;          // 32 threads
+    const int u0 = 2 * lane, u1 = u0 + 1;
+    int Tb, Ub;
+    utt_extent(d, xlen, ylen, b, Tb, Ub);
+    const size_t base = (size_t)b * lattice_block(d);
+    const int last = Tb + Ub - 2;
+    const int mU = d.maxU;
+    const unsigned w0 = u0 < Ub ? (unsigned)Tb : 0u, w1 = u1 < Ub ? (unsigned)Tb : 0u;
+    const uint32_t step_bytes = 32 * 32;   // 32 lanes x two 16-byte factor records per diagonal
+    uint32_t ring_u = ring_base + lane * 32;
+    asm volatile("" : "+r"(ring_u));
+    const int dstep = DIR * mU;
+    const int n0 = BACKWARD ? last : 0;
+    const float4* gp = fac + base + u0 + (ptrdiff_t)n0 * mU;   // column u0's record; u1's is the next one
+    LogVal* sp = out + base + u0 + (ptrdiff_t)n0 * mU;
+    int nu = n0 - u0;                      // column u0: active iff (unsigned)nu < w0; column u1: (unsigned)(nu-1) < w1
+    auto neutral = [](uint32_t addr) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %1, %3};" ::"r"(addr), "r"(0x3f800000), "r"(0), "r"(kEZero) : "memory");
+    };
+#pragma unroll
+    for (int k = 0; k < kLinRing; ++k) {
+        const bool a0 = (unsigned)(nu + k * DIR) < w0, a1 = (unsigned)(nu - 1 + k * DIR) < w1;
+        if (k < kLinRing - 1) {
+            if (a0) cp_async16_s(ring_u + k * step_bytes, gp); else neutral(ring_u + k * step_bytes);
+            if (a1) cp_async16_s(ring_u + k * step_bytes + 16, gp + 1); else neutral(ring_u + k * step_bytes + 16);
+            cp_async_commit();
+            gp += dstep;
+        } else {   // the last slot is step 0's refill target: neutral only where no copy will land
+            if (!a0) neutral(ring_u + k * step_bytes);
+            if (!a1) neutral(ring_u + k * step_bytes + 16);
+        }
+    }
+    float sv0 = 1.0f, ov0 = 1.0f, sv1 = 1.0f, ov1 = 1.0f;
+    int se0 = kEZero, oe0 = kEZero, se1 = kEZero, oe1 = kEZero;
+    if (!BACKWARD && lane == 0) se0 = 0;                       // alpha(0,0) = 1
+    if (BACKWARD && u0 == Ub - 1) se0 = 0;                     // virtual beta(T, U-1) = 1
+    if (BACKWARD && u1 == Ub - 1) se1 = 0;
+    float nansum = 0.0f;
+    const int edge_bias = (BACKWARD ? lane == 31 : lane == 0) ? kEZero : 0;
+
+    for (int s0 = 0; s0 <= last; s0 += kLinRing) {
+#pragma unroll
+        for (int j = 0; j < kLinRing; ++j) {
+            const int s = s0 + j;
+            if (s > last) break;
+            cp_async_wait<kLinRing - 2>();
+            {
+                const uint32_t slot = ring_u + ((j + kLinRing - 1) % kLinRing) * step_bytes;
+                if ((unsigned)(nu + (kLinRing - 1) * DIR) < w0) cp_async16_s(slot, gp);
+                if ((unsigned)(nu - 1 + (kLinRing - 1) * DIR) < w1) cp_async16_s(slot + 16, gp + 1);
+            }
+            cp_async_commit();
+            gp += dstep;
+            const bool a0 = (unsigned)nu < w0, a1 = (unsigned)(nu - 1) < w1;
+            const float4 f0 = lds128(ring_u + j * step_bytes), f1 = lds128(ring_u + j * step_bytes + 16);
+            nansum = fmaf(f0.x, f0.z, fmaf(f1.x, f1.z, nansum));
+            const int kb0 = __float_as_int(f0.y), kl0 = __float_as_int(f0.w);
+            const int kb1 = __float_as_int(f1.y), kl1 = __float_as_int(f1.w);
+            float v0, v1;
+            int e0, e1;
+            if (BACKWARD) {
+                // column u1's right neighbour is the next lane's u0; column u0's is this lane's u1 (previous step)
+                const float nv = __shfl_down_sync(0xffffffffu, sv0, 1);
+                const int ne = __shfl_down_sync(0xffffffffu, se0, 1) + edge_bias;
+                lin_add(sv0 * f0.x, se0 + kb0, sv1 * f0.z, se1 + kl0, v0, e0);
+                lin_add(sv1 * f1.x, se1 + kb1, nv * f1.z, ne + kl1, v1, e1);
+                sv0 = v0, se0 = e0, sv1 = v1, se1 = e1;
+            } else {
+                // column u0's left neighbour is the previous lane's u1; column u1's is this lane's u0 (previous step)
+                const float nv = __shfl_up_sync(0xffffffffu, ov1, 1);
+                const int ne = __shfl_up_sync(0xffffffffu, oe1, 1) + edge_bias;
+                lin_add(sv1, se1, ov0, oe0, v1, e1);
+                lin_add(sv0, se0, nv, ne, v0, e0);
+                sv0 = v0 * f0.x, se0 = e0 + kb0, ov0 = v0 * f0.z, oe0 = e0 + kl0;
+                sv1 = v1 * f1.x, se1 = e1 + kb1, ov1 = v1 * f1.z, oe1 = e1 + kl1;
+            }
+            if (a0) sp[0] = to_logval(v0, e0);
+            if (a1) sp[1] = to_logval(v1, e1);
+            sp += dstep;
+            nu += DIR;
+        }
+    }
+    cp_async_wait<0>();
+    const bool bad = __any_sync(0xffffffffu, nansum != nansum);
+    if (!BACKWARD) {
+        if (u0 == Ub - 1 || u1 == Ub - 1) {
+            const bool first = u0 == Ub - 1;
+            const float v = first ? sv0 : sv1;
+            const int e = first ? se0 : se1;
+            LogVal ll = to_logval(v, e);
+            float cost = -(logval_log2(ll) * 0.6931471805599453f);
+            if (e < kEDead) cost = INFINITY;
+            if (bad) {
+                cost = __int_as_float(0x7fc00000);
+                ll.l = cost;
+            }
+            llout[b] = ll;
+            costs[b] = cost;
+        }
+    } else if (lane == 0) {
+        LogVal ll = to_logval(sv0, se0);
+        if (bad) ll.l = __int_as_float(0x7fc00000);
+        llout[b] = ll;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+lattice_lin2_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen, const int* __restrict__ ylen,
+                    LogVal* __restrict__ alphas, LogVal* __restrict__ betas, LogVal* __restrict__ llf,
+                    LogVal* __restrict__ llb, float* __restrict__ costs, const Dims d) {
+    __shared__ __align__(16) unsigned char ring_raw[kLinRing * 32 * 32];
+    const uint32_t ring_base = smem_u32(ring_raw);
+    pdl_trigger();
+    pdl_wait();
+    if (blockIdx.y == 0) lattice_lin_body2<false>(fac, xlen, ylen, alphas, llf, costs, d, ring_base);
+    else lattice_lin_body2<true>(fac, xlen, ylen, betas, llb, costs, d, ring_base);
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(1024)
 lattice_lin_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen, const int* __restrict__ ylen,
