@@ -82,18 +82,24 @@ void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
     cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
-// cudaFuncSetAttribute once per (kernel, attribute, device) and host thread.  Keyed by the kernel's
+// cudaFuncSetAttribute once per (kernel, attribute, device) and host thread (again only for a larger value).  Keyed by the kernel's
 // address: template instantiations with identical signatures share a function-pointer TYPE, so a static
 // flag inside a generic lambda would be shared between them.
 void func_attr_once(const void* kernel, cudaFuncAttribute attr, int value) {
-    struct Key { const void* k; int attr, dev; };
+    struct Key { const void* k; int attr, dev, value; };
     thread_local std::vector<Key> done;
     int dev = 0;
     cudaGetDevice(&dev);
-    for (const Key& e : done)
-        if (e.k == kernel && e.attr == (int)attr && e.dev == dev) return;
+    for (Key& e : done)
+        if (e.k == kernel && e.attr == (int)attr && e.dev == dev) {
+            if (value > e.value) {   // e.g. a larger dynamic shared-memory request than any before
+                cudaFuncSetAttribute(kernel, attr, value);
+                e.value = value;
+            }
+            return;
+        }
     cudaFuncSetAttribute(kernel, attr, value);
-    done.push_back(Key{kernel, (int)attr, dev});
+    done.push_back(Key{kernel, (int)attr, dev, value});
 }
 
 // Side streams for overlapping the (latency-bound, few-SM) lattice kernel of one group of
@@ -505,23 +511,19 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         const int threads = (opt.maxU + 31) / 32 * 32;
         dim3 grid(g.d.N, with_beta ? 2 : 1);
         if constexpr (sizeof(T) == 4) {
-            // fp32: linear-domain wavefront with explicit exponents (rnnt_lattice.cuh)
-            const size_t ring = (size_t)kLinRing * threads * sizeof(float4);
+            // fp32: linear-domain wavefront with explicit exponents, COLS columns per lane (rnnt_lattice.cuh)
+            const int lthreads = lattice_threads(opt.maxU);
+            const size_t ring = lattice_ring_bytes(opt.maxU);
             auto launch = [&](auto kernel, int static_smem) {
                 if (ring + static_smem > 48 * 1024)
-                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
-                launch_k(kernel, grid, dim3(threads), ring, st, g_pdl, static_cast<const float4*>(g.w.lp2), g.xlen, g.ylen,
+                    func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+                launch_k(kernel, grid, dim3(lthreads), ring, st, g_pdl, static_cast<const float4*>(g.w.lp2), g.xlen, g.ylen,
                          static_cast<LogVal*>(g.w.alphas), static_cast<LogVal*>(g.w.betas), static_cast<LogVal*>(g.w.llf),
                          static_cast<LogVal*>(g.w.llb), g.costs, g.d);
             };
-            static const bool two_col = [] { const char* e = getenv("RNNT_B200_LATTICE2"); return !(e && atoi(e) == 0); }();
-            if (threads > 32 && opt.maxU <= 64 && two_col) {
-                // 33..64 labels: one warp per direction, two columns per lane, no cross-warp exchange
-                launch_k(lattice_lin2_kernel, grid, dim3(32), 0, st, g_pdl, static_cast<const float4*>(g.w.lp2), g.xlen,
-                         g.ylen, static_cast<LogVal*>(g.w.alphas), static_cast<LogVal*>(g.w.betas),
-                         static_cast<LogVal*>(g.w.llf), static_cast<LogVal*>(g.w.llb), g.costs, g.d);
-            } else if (threads > 32) launch(lattice_lin_kernel<true>, kLinStaticSmem);
-            else launch(lattice_lin_kernel<false>, 64);
+            if (opt.maxU <= 32) launch(lattice_lin_kernel<1, false>, 64);
+            else if (opt.maxU <= 64) launch(lattice_lin_kernel<2, false>, 64);
+            else launch(lattice_lin_kernel<1, true>, kLinStaticSmem);
         } else {
             // fp64: log-domain wavefront (rnnt_kernels.cuh)
             const size_t ring = (size_t)kRing * threads * sizeof(double2);
@@ -761,16 +763,17 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     }
     // lattice (same kernel as the dense path)
     {
-        const int threads = (U + 31) / 32 * 32;
         dim3 grid(N, with_beta ? 2 : 1);
-        const size_t ring = (size_t)kLinRing * threads * sizeof(float4);
+        const int lthreads = lattice_threads(U);
+        const size_t ring = lattice_ring_bytes(U);
         auto launch = [&](auto kernel, int static_smem) {
             if (ring + static_smem > 48 * 1024)
-                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
-            kernel<<<grid, threads, ring, s>>>(w.lp2, xlen, ylen, w.alphas, w.betas, w.llf, w.llb, costs, d);
+                func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+            kernel<<<grid, lthreads, ring, s>>>(w.lp2, xlen, ylen, w.alphas, w.betas, w.llf, w.llb, costs, d);
         };
-        if (threads > 32) launch(lattice_lin_kernel<true>, kLinStaticSmem);
-        else launch(lattice_lin_kernel<false>, 64);
+        if (U <= 32) launch(lattice_lin_kernel<1, false>, 64);
+        else if (U <= 64) launch(lattice_lin_kernel<2, false>, 64);
+        else launch(lattice_lin_kernel<1, true>, kLinStaticSmem);
     }
     g_last_launches += 5;
     }  // phase != kBackward

@@ -81,11 +81,18 @@ __device__ __forceinline__ void sts_volatile(uint32_t addr, int v) {
 }
 
 // =================================================================================================
-// grid = (N, 1 or 2): blockIdx.y 0 -> alpha, 1 -> beta.  One thread per u, blockDim = maxU rounded up
-// to a warp.  Step s = 0..last visits anti-diagonal n = s (alpha) or n = last - s (beta); thread u
-// owns cell (n - u, u).
+// grid = (N, 1 or 2): blockIdx.y 0 -> alpha, 1 -> beta.  Every lane owns COLS ADJACENT columns
+// (u = (thread * COLS) + c), a warp 32*COLS of them; blockDim = ceil(maxU / (32*COLS)) warps.
+// Step s = 0..last visits anti-diagonal n = s (alpha) or n = last - s (beta); column u owns cell (n-u, u).
+//
+// Why several columns per lane: the neighbour of a lane's inner columns is the lane's own adjacent
+// column from the previous step (a register), only the first (alpha) / last (beta) column's neighbour
+// crosses lanes - ONE shuffle pair per step serves COLS cells, the COLS cell updates are independent
+// (ILP), and a wavefront of U columns needs U/(32*COLS) warps instead of U/32: with two columns per
+// lane 33..64 labels are a single warp with no cross-warp exchange at all.
+// (See lattice_cols() for when that pays and when it does not.)
 // =================================================================================================
-template <bool MULTI, bool BACKWARD>
+template <int COLS, bool MULTI, bool BACKWARD>
 __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac, const int* __restrict__ xlen,
                                                  const int* __restrict__ ylen, LogVal* __restrict__ out,
                                                  LogVal* __restrict__ llout, float* __restrict__ costs,
@@ -93,55 +100,64 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
                                                  uint32_t prog_base, int* bad_any) {
     constexpr int DIR = BACKWARD ? -1 : 1;
     const int b = blockIdx.x;
-    const int u = threadIdx.x;
+    const int tid = threadIdx.x;
     const int NT = blockDim.x;
-    const int lane = u & 31;
+    const int lane = tid & 31;
     // broadcast from lane 0 so the compiler treats the warp index (and everything derived from it:
     // has_src / has_dst, the exchange addresses) as warp-uniform - no divergence handling in the step loop
-    const int warp = __shfl_sync(0xffffffffu, u >> 5, 0);
+    const int warp = MULTI ? __shfl_sync(0xffffffffu, tid >> 5, 0) : 0;
+    const int u0 = tid * COLS;             // first column of this lane
     int Tb, Ub;
     utt_extent(d, xlen, ylen, b, Tb, Ub);
     const size_t base = (size_t)b * lattice_block(d);
     const int last = Tb + Ub - 2;
     const int mU = d.maxU;
-    const int nactive = (Ub + 31) >> 5;   // warps that own at least one column
-    if (MULTI && warp >= nactive) return;  // no column of this warp exists in this utterance
+    const int nactive = (Ub + 32 * COLS - 1) / (32 * COLS);   // warps that own at least one column
+    if (MULTI && warp >= nactive) return;                     // no column of this warp exists in this utterance
 
-    const unsigned width = u < Ub ? (unsigned)Tb : 0u;   // thread u is active on diagonals n with n - u < width
-    const uint32_t step_bytes = NT * 16;
-    uint32_t ring_u = ring_base + u * 16;                // this thread's column of the ring
+    unsigned width[COLS];                  // column c is active on diagonals n with (unsigned)(n - u0 - c) < width[c]
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) width[c] = u0 + c < Ub ? (unsigned)Tb : 0u;
+    const uint32_t step_bytes = NT * COLS * 16;
+    uint32_t ring_u = ring_base + tid * (COLS * 16);     // this thread's COLS records of a ring slot
     asm volatile("" : "+r"(ring_u));                     // opaque: keep it in a register, do not rematerialise the cvta
     const int dstep = DIR * mU;                          // pointer step per diagonal in step order
     const int n0 = BACKWARD ? last : 0;
-    const float4* gp = fac + base + u + (ptrdiff_t)n0 * mU;  // next diagonal to fetch
-    LogVal* sp = out + base + u + (ptrdiff_t)n0 * mU;
-    int nu = n0 - u;                                     // (current diagonal) - u: active iff (unsigned)nu < width
-    // Ring slots that no copy will fill hold NEUTRAL factors: the step body below runs unconditionally - a
-    // column that is not active yet keeps its "log zero" unchanged, a column that has finished computes
-    // values nobody reads - and only the lattice STORE is predicated.
+    const float4* gp = fac + base + u0 + (ptrdiff_t)n0 * mU;  // column u0's record of the next diagonal to fetch
+    LogVal* sp = out + base + u0 + (ptrdiff_t)n0 * mU;
+    int nu = n0 - u0;                                    // (current diagonal) - u0
+    // Ring slots that no copy will fill hold NEUTRAL factors {1, 0, 1, log zero}: the step body below runs
+    // unconditionally - a column that is not active yet keeps its "log zero" unchanged (and beta's virtual
+    // beta(T,U-1) = 1 in column U-1 cannot leak into column U-2), a column that has finished computes values
+    // nobody reads - and only the lattice STORE is predicated.
+    auto neutral = [](uint32_t addr) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %1, %3};" ::"r"(addr), "r"(0x3f800000), "r"(0), "r"(kEZero) : "memory");
+    };
 #pragma unroll
     for (int k = 0; k < kLinRing; ++k) {
-        if (k < kLinRing - 1 && (unsigned)(nu + k * DIR) < width) {
-            cp_async16_s(ring_u + k * step_bytes, gp);
-        } else if (k < kLinRing - 1 || !((unsigned)(nu + k * DIR) < width)) {   // (the last slot is step 0's refill target)
-            // {m_blank, k_blank, m_label, k_label} = {1, 0, 1, log zero}: the "stay" factor is the identity, the
-            // "emit" factor kills the neighbour's contribution (beta's virtual beta(T,U-1) = 1 sits in column
-            // U-1 from the start and must not leak into column U-2 before that column becomes active)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %1, %3};" ::"r"(ring_u + k * step_bytes), "r"(0x3f800000), "r"(0),
-                         "r"(kEZero)
-                         : "memory");
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+            const bool act = (unsigned)(nu - c + k * DIR) < width[c];
+            const uint32_t slot = ring_u + k * step_bytes + c * 16;
+            if (k < kLinRing - 1 && act) cp_async16_s(slot, gp + c);
+            else if (k < kLinRing - 1 || !act) neutral(slot);   // (the last slot is step 0's refill target)
         }
         if (k < kLinRing - 1) {
             cp_async_commit();
             gp += dstep;
         }
     }
-    // running value.  alpha: (sv,se) = alpha(t,u) p_blank(t,u) offered to (t+1,u), (ov,oe) = alpha(t,u)
+    // running values.  alpha: (sv,se) = alpha(t,u) p_blank(t,u) offered to (t+1,u), (ov,oe) = alpha(t,u)
     // p_label(t,u) offered to (t,u+1).  beta: (sv,se) = beta(t+1,u).
-    float sv = 1.0f, ov = 1.0f;
-    int se = kEZero, oe = kEZero;
-    if (!BACKWARD && u == 0) se = 0;                     // alpha(0,0) = 1 enters as the "stay" term of step 0
-    if (BACKWARD && u == Ub - 1) se = 0;                 // virtual beta(T, U-1) = 1
+    float sv[COLS], ov[COLS];
+    int se[COLS], oe[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+        sv[c] = ov[c] = 1.0f;
+        se[c] = oe[c] = kEZero;
+        if (!BACKWARD && u0 + c == 0) se[c] = 0;        // alpha(0,0) = 1 enters as the "stay" term of step 0
+        if (BACKWARD && u0 + c == Ub - 1) se[c] = 0;    // virtual beta(T, U-1) = 1
+    }
     float nansum = 0.0f;                                 // NaN factor anywhere -> NaN here
     // cross-warp neighbour (warp-uniform): alpha reads warp-1's lane 31, beta reads warp+1's lane 0
     const bool has_src = MULTI && (BACKWARD ? warp + 1 < nactive : warp > 0);
@@ -168,22 +184,25 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
             if (s > last) break;
             cp_async_wait<kLinRing - 2>();   // this thread's factors of the current diagonal have landed
             // refill the slot of the previous step (private to this thread, already consumed)
-            if ((unsigned)(nu + (kLinRing - 1) * DIR) < width)
-                cp_async16_s(ring_u + ((j + kLinRing - 1) % kLinRing) * step_bytes, gp);
+#pragma unroll
+            for (int c = 0; c < COLS; ++c)
+                if ((unsigned)(nu - c + (kLinRing - 1) * DIR) < width[c])
+                    cp_async16_s(ring_u + ((j + kLinRing - 1) % kLinRing) * step_bytes + c * 16, gp + c);
             cp_async_commit();
             gp += dstep;
-            const bool active = (unsigned)nu < width;
-            const float4 f = lds128(ring_u + j * step_bytes);   // identity / stale factors when not active
+            float4 f[COLS];   // neutral / stale factors where a column is not active
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) f[c] = lds128(ring_u + j * step_bytes + c * 16);
 
-            // neighbour's value from the previous step
+            // the one neighbour value that crosses lanes, from the previous step
             float nv;
             int ne;
             if (BACKWARD) {
-                nv = __shfl_down_sync(0xffffffffu, sv, 1);
-                ne = __shfl_down_sync(0xffffffffu, se, 1);
+                nv = __shfl_down_sync(0xffffffffu, sv[0], 1);
+                ne = __shfl_down_sync(0xffffffffu, se[0], 1);
             } else {
-                nv = __shfl_up_sync(0xffffffffu, ov, 1);
-                ne = __shfl_up_sync(0xffffffffu, oe, 1);
+                nv = __shfl_up_sync(0xffffffffu, ov[COLS - 1], 1);
+                ne = __shfl_up_sync(0xffffffffu, oe[COLS - 1], 1);
             }
             if (MULTI && has_src) {
                 // value of step s-1 (tag s) from the neighbouring warp; at s == 0 nothing beside is active
@@ -194,28 +213,46 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
             } else {
                 ne += edge_bias;   // the lane without a neighbour: push its (own, shuffled-back) value to log zero
             }
-            {
-                nansum = fmaf(f.x, f.z, nansum);
-                const int kb = __float_as_int(f.y), kl = __float_as_int(f.w);
-                float v;
-                int e;
-                if (BACKWARD) {
-                    // beta(t,u) = beta(t+1,u) p_blank(t,u) + beta(t,u+1) p_label(t,u)
-                    lin_add(sv * f.x, se + kb, nv * f.z, ne + kl, v, e);
-                    sv = v, se = e;
-                } else {
-                    // alpha(t,u) = [alpha(t-1,u) p_blank(t-1,u)] + [alpha(t,u-1) p_label(t,u-1)]
-                    lin_add(sv, se, nv, ne, v, e);
-                    sv = v * f.x, se = e + kb;   // offered to (t+1, u)
-                    ov = v * f.z, oe = e + kl;   // offered to (t, u+1)
+            float v[COLS];
+            int e[COLS];
+            if (BACKWARD) {
+                // beta(t,u) = beta(t+1,u) p_blank(t,u) + beta(t,u+1) p_label(t,u);  (t,u+1): the next column of
+                // this lane (previous step's value), or the next lane's first column for the last one
+#pragma unroll
+                for (int c = 0; c < COLS; ++c) {
+                    const float rv = c + 1 < COLS ? sv[c + 1 < COLS ? c + 1 : c] : nv;
+                    const int re = c + 1 < COLS ? se[c + 1 < COLS ? c + 1 : c] : ne;
+                    lin_add(sv[c] * f[c].x, se[c] + __float_as_int(f[c].y), rv * f[c].z, re + __float_as_int(f[c].w), v[c], e[c]);
                 }
-                if (active) *sp = to_logval(v, e);
+#pragma unroll
+                for (int c = 0; c < COLS; ++c) sv[c] = v[c], se[c] = e[c];
+            } else {
+                // alpha(t,u) = [alpha(t-1,u) p_blank(t-1,u)] + [alpha(t,u-1) p_label(t,u-1)];  (t,u-1): the previous
+                // column of this lane (previous step's offer), or the previous lane's last column for the first one
+#pragma unroll
+                for (int c = 0; c < COLS; ++c) {
+                    const float lv = c > 0 ? ov[c > 0 ? c - 1 : 0] : nv;
+                    const int le = c > 0 ? oe[c > 0 ? c - 1 : 0] : ne;
+                    lin_add(sv[c], se[c], lv, le, v[c], e[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < COLS; ++c) {
+                    sv[c] = v[c] * f[c].x, se[c] = e[c] + __float_as_int(f[c].y);   // offered to (t+1, u)
+                    ov[c] = v[c] * f[c].z, oe[c] = e[c] + __float_as_int(f[c].w);   // offered to (t, u+1)
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) {
+                nansum = fmaf(f[c].x, f[c].z, nansum);
+                if ((unsigned)(nu - c) < width[c]) sp[c] = to_logval(v[c], e[c]);
             }
             sp += dstep;
             nu += DIR;
             if (MULTI) {
                 const uint32_t slot_off = (eoff + (uint32_t)j * 16) & (kEdge * 16 - 1);
-                if (has_dst) edge_publish(my_edge + slot_off, BACKWARD ? sv : ov, BACKWARD ? se : oe, s + 1, pub_lane);
+                if (has_dst)
+                    edge_publish(my_edge + slot_off, BACKWARD ? sv[0] : ov[COLS - 1], BACKWARD ? se[0] : oe[COLS - 1], s + 1,
+                                 pub_lane);
                 if (has_src) {
                     sts_volatile(prog_base + warp * 4, s);   // every lane, same value: progress of this warp
                     pok = __all_sync(0xffffffffu, edge_read(src_edge + slot_off, s + 1, pv, pe));   // prefetch for the next step
@@ -235,11 +272,16 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
         bad = __any_sync(0xffffffffu, bad);
     }
     if (!BACKWARD) {
-        if (u == Ub - 1) {
-            // sv, se = alpha(T-1,U-1) p_blank(T-1,U-1) after the last step
-            LogVal ll = to_logval(sv, se);
+        // (sv, se) of column U-1 = alpha(T-1,U-1) p_blank(T-1,U-1) after the last step
+        if ((Ub - 1) / COLS == tid) {
+            float fv = sv[0];
+            int fe = se[0];
+#pragma unroll
+            for (int c = 1; c < COLS; ++c)
+                if ((Ub - 1) % COLS == c) fv = sv[c], fe = se[c];
+            LogVal ll = to_logval(fv, fe);
             float cost = -(logval_log2(ll) * 0.6931471805599453f);
-            if (se < kEDead) cost = INFINITY;
+            if (fe < kEDead) cost = INFINITY;
             if (bad) {
                 cost = __int_as_float(0x7fc00000);
                 ll.l = cost;
@@ -247,151 +289,19 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
             llout[b] = ll;
             costs[b] = cost;
         }
-    } else if (u == 0) {
-        LogVal ll = to_logval(sv, se);
+    } else if (tid == 0) {
+        LogVal ll = to_logval(sv[0], se[0]);
         if (bad) ll.l = __int_as_float(0x7fc00000);
         llout[b] = ll;
     }
 }
 
-// =================================================================================================
-// 32 < maxU <= 64: ONE warp per direction, TWO adjacent columns per lane (u0 = 2*lane, u1 = u0 + 1).
-// The neighbour of the second column is the lane's own first column (a register), only the first
-// column's neighbour crosses lanes - one shuffle pair per step serves two cells, the two cell updates are
-// independent (ILP 2), and there is no cross-warp exchange at all.  Same arithmetic, ring and neutral-
-// factor conventions as lattice_lin_body.
-// =================================================================================================
-template <bool BACKWARD>
-__device__ __forceinline__ void lattice_lin_body2(const float4* __restrict__ fac, const int* __restrict__ xlen,
-                                                  const int* __restrict__ ylen, LogVal* __restrict__ out,
-                                                  LogVal* __restrict__ llout, float* __restrict__ costs,
-                                                  const Dims& d, uint32_t ring_base) {
-    constexpr int DIR = BACKWARD ? -1 : 1;
-    const int b = blockIdx.x;
-    const int lane = threadIdx.x;          // 32 threads
-    const int u0 = 2 * lane, u1 = u0 + 1;
-    int Tb, Ub;
-    utt_extent(d, xlen, ylen, b, Tb, Ub);
-    const size_t base = (size_t)b * lattice_block(d);
-    const int last = Tb + Ub - 2;
-    const int mU = d.maxU;
-    const unsigned w0 = u0 < Ub ? (unsigned)Tb : 0u, w1 = u1 < Ub ? (unsigned)Tb : 0u;
-    const uint32_t step_bytes = 32 * 32;   // 32 lanes x two 16-byte factor records per diagonal
-    uint32_t ring_u = ring_base + lane * 32;
-    asm volatile("" : "+r"(ring_u));
-    const int dstep = DIR * mU;
-    const int n0 = BACKWARD ? last : 0;
-    const float4* gp = fac + base + u0 + (ptrdiff_t)n0 * mU;   // column u0's record; u1's is the next one
-    LogVal* sp = out + base + u0 + (ptrdiff_t)n0 * mU;
-    int nu = n0 - u0;                      // column u0: active iff (unsigned)nu < w0; column u1: (unsigned)(nu-1) < w1
-    auto neutral = [](uint32_t addr) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %1, %3};" ::"r"(addr), "r"(0x3f800000), "r"(0), "r"(kEZero) : "memory");
-    };
-#pragma unroll
-    for (int k = 0; k < kLinRing; ++k) {
-        const bool a0 = (unsigned)(nu + k * DIR) < w0, a1 = (unsigned)(nu - 1 + k * DIR) < w1;
-        if (k < kLinRing - 1) {
-            if (a0) cp_async16_s(ring_u + k * step_bytes, gp); else neutral(ring_u + k * step_bytes);
-            if (a1) cp_async16_s(ring_u + k * step_bytes + 16, gp + 1); else neutral(ring_u + k * step_bytes + 16);
-            cp_async_commit();
-            gp += dstep;
-        } else {   // the last slot is step 0's refill target: neutral only where no copy will land
-            if (!a0) neutral(ring_u + k * step_bytes);
-            if (!a1) neutral(ring_u + k * step_bytes + 16);
-        }
-    }
-    float sv0 = 1.0f, ov0 = 1.0f, sv1 = 1.0f, ov1 = 1.0f;
-    int se0 = kEZero, oe0 = kEZero, se1 = kEZero, oe1 = kEZero;
-    if (!BACKWARD && lane == 0) se0 = 0;                       // alpha(0,0) = 1
-    if (BACKWARD && u0 == Ub - 1) se0 = 0;                     // virtual beta(T, U-1) = 1
-    if (BACKWARD && u1 == Ub - 1) se1 = 0;
-    float nansum = 0.0f;
-    const int edge_bias = (BACKWARD ? lane == 31 : lane == 0) ? kEZero : 0;
-
-    for (int s0 = 0; s0 <= last; s0 += kLinRing) {
-#pragma unroll
-        for (int j = 0; j < kLinRing; ++j) {
-            const int s = s0 + j;
-            if (s > last) break;
-            cp_async_wait<kLinRing - 2>();
-            {
-                const uint32_t slot = ring_u + ((j + kLinRing - 1) % kLinRing) * step_bytes;
-                if ((unsigned)(nu + (kLinRing - 1) * DIR) < w0) cp_async16_s(slot, gp);
-                if ((unsigned)(nu - 1 + (kLinRing - 1) * DIR) < w1) cp_async16_s(slot + 16, gp + 1);
-            }
-            cp_async_commit();
-            gp += dstep;
-            const bool a0 = (unsigned)nu < w0, a1 = (unsigned)(nu - 1) < w1;
-            const float4 f0 = lds128(ring_u + j * step_bytes), f1 = lds128(ring_u + j * step_bytes + 16);
-            nansum = fmaf(f0.x, f0.z, fmaf(f1.x, f1.z, nansum));
-            const int kb0 = __float_as_int(f0.y), kl0 = __float_as_int(f0.w);
-            const int kb1 = __float_as_int(f1.y), kl1 = __float_as_int(f1.w);
-            float v0, v1;
-            int e0, e1;
-            if (BACKWARD) {
-                // column u1's right neighbour is the next lane's u0; column u0's is this lane's u1 (previous step)
-                const float nv = __shfl_down_sync(0xffffffffu, sv0, 1);
-                const int ne = __shfl_down_sync(0xffffffffu, se0, 1) + edge_bias;
-                lin_add(sv0 * f0.x, se0 + kb0, sv1 * f0.z, se1 + kl0, v0, e0);
-                lin_add(sv1 * f1.x, se1 + kb1, nv * f1.z, ne + kl1, v1, e1);
-                sv0 = v0, se0 = e0, sv1 = v1, se1 = e1;
-            } else {
-                // column u0's left neighbour is the previous lane's u1; column u1's is this lane's u0 (previous step)
-                const float nv = __shfl_up_sync(0xffffffffu, ov1, 1);
-                const int ne = __shfl_up_sync(0xffffffffu, oe1, 1) + edge_bias;
-                lin_add(sv1, se1, ov0, oe0, v1, e1);
-                lin_add(sv0, se0, nv, ne, v0, e0);
-                sv0 = v0 * f0.x, se0 = e0 + kb0, ov0 = v0 * f0.z, oe0 = e0 + kl0;
-                sv1 = v1 * f1.x, se1 = e1 + kb1, ov1 = v1 * f1.z, oe1 = e1 + kl1;
-            }
-            if (a0) sp[0] = to_logval(v0, e0);
-            if (a1) sp[1] = to_logval(v1, e1);
-            sp += dstep;
-            nu += DIR;
-        }
-    }
-    cp_async_wait<0>();
-    const bool bad = __any_sync(0xffffffffu, nansum != nansum);
-    if (!BACKWARD) {
-        if (u0 == Ub - 1 || u1 == Ub - 1) {
-            const bool first = u0 == Ub - 1;
-            const float v = first ? sv0 : sv1;
-            const int e = first ? se0 : se1;
-            LogVal ll = to_logval(v, e);
-            float cost = -(logval_log2(ll) * 0.6931471805599453f);
-            if (e < kEDead) cost = INFINITY;
-            if (bad) {
-                cost = __int_as_float(0x7fc00000);
-                ll.l = cost;
-            }
-            llout[b] = ll;
-            costs[b] = cost;
-        }
-    } else if (lane == 0) {
-        LogVal ll = to_logval(sv0, se0);
-        if (bad) ll.l = __int_as_float(0x7fc00000);
-        llout[b] = ll;
-    }
-}
-
-__global__ void __launch_bounds__(32)
-lattice_lin2_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen, const int* __restrict__ ylen,
-                    LogVal* __restrict__ alphas, LogVal* __restrict__ betas, LogVal* __restrict__ llf,
-                    LogVal* __restrict__ llb, float* __restrict__ costs, const Dims d) {
-    __shared__ __align__(16) unsigned char ring_raw[kLinRing * 32 * 32];
-    const uint32_t ring_base = smem_u32(ring_raw);
-    pdl_trigger();
-    pdl_wait();
-    if (blockIdx.y == 0) lattice_lin_body2<false>(fac, xlen, ylen, alphas, llf, costs, d, ring_base);
-    else lattice_lin_body2<true>(fac, xlen, ylen, betas, llb, costs, d, ring_base);
-}
-
-template <bool MULTI>
-__global__ void __launch_bounds__(1024)
+template <int COLS, bool MULTI>
+__global__ void __launch_bounds__(MULTI ? 1024 / COLS : 32)
 lattice_lin_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen, const int* __restrict__ ylen,
                    LogVal* __restrict__ alphas, LogVal* __restrict__ betas, LogVal* __restrict__ llf,
                    LogVal* __restrict__ llb, float* __restrict__ costs, const Dims d) {
-    extern __shared__ __align__(16) unsigned char ring_raw[];   // [kLinRing][blockDim.x] float4, thread-private columns
+    extern __shared__ __align__(16) unsigned char ring_raw[];   // [kLinRing][blockDim.x][COLS] float4, thread-private
     __shared__ __align__(16) int4 edge[MULTI ? kEdgeWarps * kEdge : 1];
     __shared__ int prog[MULTI ? kEdgeWarps : 1];
     __shared__ int bad_any;
@@ -406,9 +316,21 @@ lattice_lin_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen,
     pdl_trigger();   // the gradient kernel may launch and read the logits while the wavefront runs
     pdl_wait();      // pass 1's factors are complete and visible
     if (blockIdx.y == 0)
-        lattice_lin_body<MULTI, false>(fac, xlen, ylen, alphas, llf, costs, d, ring_base, edge_base, prog_base, &bad_any);
+        lattice_lin_body<COLS, MULTI, false>(fac, xlen, ylen, alphas, llf, costs, d, ring_base, edge_base, prog_base, &bad_any);
     else
-        lattice_lin_body<MULTI, true>(fac, xlen, ylen, betas, llb, costs, d, ring_base, edge_base, prog_base, &bad_any);
+        lattice_lin_body<COLS, MULTI, true>(fac, xlen, ylen, betas, llb, costs, d, ring_base, edge_base, prog_base, &bad_any);
 }
+
+// Columns per lane for a label extent.  Measured on B200: a lone warp issues one instruction every 3-4
+// cycles whatever the instruction-level parallelism, so a warp-step costs ~4 cycles x its instruction count:
+//   U = 41 : 2 warps x 1 column (with the cross-warp exchange) 41 us,  1 warp x 2 columns 26 us
+//   U = 301: 10 warps x 1 column 0.43 ms,  3 warps x 4 columns 0.51 ms
+// -> two columns per lane exactly where that saves the exchange (33..64 labels), one column otherwise.
+inline int lattice_cols(int maxU) { return maxU > 32 && maxU <= 64 ? 2 : 1; }
+inline int lattice_threads(int maxU) {
+    const int per_warp = 32 * lattice_cols(maxU);
+    return (maxU + per_warp - 1) / per_warp * 32;
+}
+inline size_t lattice_ring_bytes(int maxU) { return (size_t)kLinRing * lattice_threads(maxU) * lattice_cols(maxU) * 16; }
 
 }  // namespace b200rnnt
