@@ -11,9 +11,11 @@
 //     (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP): no per-element load instructions, no
 //     alignment cases, the address generation is off the SM's issue slots.
 //   * While the copy is in flight every thread decodes its row and fetches the per-row scalars.
-//   * TPR threads share a row and walk it from shared memory element by element; TPR is the power
-//     of two dividing V (V=50 -> 2, V=28 -> 4), which makes the interleaved walk bank-conflict free
-//     (lane (i,h) touches word i*V + h + j*TPR: distinct banks across the warp).
+//   * TPR threads share a row and walk it from shared memory element by element (pairs for even V); TPR
+//     is the power of two dividing V (V=50 -> 2, V=28 -> 4).  Which lanes of a warp share a row is chosen
+//     on the host per shape (ChunkMap below) so that a warp-wide access hits distinct banks: with adjacent
+//     lanes sharing a row, V=50 puts lane (row 7, slice 1) on the banks of (row 0, slice 0) - every
+//     access of the sweep took two wavefronts instead of one (ncu source page, round 2).
 //   * Pass 2 overwrites the chunk in place with the gradient and ONE thread writes it back with a
 //     bulk shared -> global copy.
 //
@@ -62,6 +64,20 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 template <typename T> struct ChunkThreads { static constexpr int value = sizeof(T) >= 8 ? 128 : 256; };
 
+// lane -> (row of the chunk, slice of the row).  slice-major (hmajor): lanes l, l + 32/TPR, ... share a
+// row, so consecutive lanes walk consecutive rows; row-major: adjacent lanes share a row.
+template <int TPR> struct ChunkMap {
+    int row, slice, stride;   // stride: lane distance between the lanes of one row
+    __device__ __forceinline__ ChunkMap(int hmajor) {
+        constexpr int RPW = 32 / TPR;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int il = hmajor ? lane % RPW : lane / TPR;
+        slice = hmajor ? lane / RPW : lane % TPR;
+        row = warp * RPW + il;
+        stride = hmajor ? RPW : 1;
+    }
+};
+
 // Stage rows [r0, r0+nrows) of the activation tensor into `tile`; returns after the data is visible
 // to every thread of the CTA.  Thread 0 has already decided that the chunk is worth reading.
 template <typename T>
@@ -88,10 +104,11 @@ template <typename T, int TPR, int NT>
 __global__ void __launch_bounds__(NT)
 rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels, const int* __restrict__ xlen,
                       const int* __restrict__ ylen, typename Real<T>::pair* __restrict__ stat,
-                      typename Lat<T>::fac* __restrict__ lp2, const Dims d) {
+                      typename Lat<T>::fac* __restrict__ lp2, const Dims d, const int hmajor) {
     using R = Real<T>;
     using Pair = typename R::pair;
     constexpr int ROWS = NT / TPR;
+    static_assert(TPR <= 32 && NT % 32 == 0, "the lanes of a row sit in one warp");
     extern __shared__ __align__(128) unsigned char chunk_raw[];
     T* tile = reinterpret_cast<T*>(chunk_raw);
     __shared__ __align__(8) unsigned long long bar_store;
@@ -136,7 +153,8 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
     // group-parallel walk.  Even V: a row is walked as PAIRS (one 8/16-byte shared-memory access per two
     // elements); the row start is pair-aligned because V is even.  Rows past the chunk walk row 0.
     {
-        const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
+        const ChunkMap<TPR> map(hmajor);
+        const int i = map.row, h = map.slice;
         const T* x = tile + (size_t)((uint32_t)i < nrows ? i : 0) * V;
         const Pair* x2 = reinterpret_cast<const Pair*>(x);
         const bool paired = (V & 1) == 0;
@@ -151,7 +169,7 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
 #pragma unroll 4
             for (int k = h; k < V; k += TPR) m = R::max(m, x[k]);
         }
-        const T M = group_max<TPR>(m);
+        const T M = group_max_strided<TPR>(m, map.stride);
         const ExpSum<T> es((M == R::neg_inf()) ? T(0) : M);
         T sum = 0;
         if (paired) {
@@ -164,7 +182,7 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
 #pragma unroll 4
             for (int k = h; k < V; k += TPR) sum += es.term(x[k]);
         }
-        const T S = group_sum<TPR>(sum);
+        const T S = group_sum_strided<TPR>(sum, map.stride);
         if (h == 0) {
             Pair ms;
             ms.x = M;
@@ -208,14 +226,15 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
                   const int* __restrict__ xlen, const int* __restrict__ ylen,
                   const typename Real<T>::pair* __restrict__ stat, const typename Lat<T>::val* __restrict__ alphas,
                   const typename Lat<T>::val* __restrict__ betas, const typename Lat<T>::val* __restrict__ llf, const T scale_in,
-                  const T* __restrict__ scale_vec, const Dims d) {
+                  const T* __restrict__ scale_vec, const Dims d, const int hmajor) {
     using R = Real<T>;
     using Pair = typename R::pair;
     constexpr int ROWS = NT / TPR;
     extern __shared__ __align__(128) unsigned char chunk_raw[];
     T* tile = reinterpret_cast<T*>(chunk_raw);
     __shared__ __align__(8) unsigned long long bar_store;
-    __shared__ ChunkRow<T> rowc[1];   // (ROWS entries if ROWPAR is switched on)
+    __shared__ ChunkRow<T> rowc[1];
+    const ChunkMap<TPR> map(hmajor);   // (ROWS entries if ROWPAR is switched on)
     const uint32_t bar = smem_u32(&bar_store);
     // chunks in reverse order: the tail of pass 1 is met first in L2
     const uint32_t nchunks = gridDim.x;
@@ -274,7 +293,7 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
             rowc[threadIdx.x] = c;
         }
     } else {
-        g = fetch(threadIdx.x / TPR);
+        g = fetch(map.row);
         valid = g.valid > 0;
     }
     // one barrier: publishes the mbarrier and the row constants, and tells whether any row is a real cell
@@ -302,7 +321,7 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
 
     // Lanes sharing a row sit in one warp (TPR divides 32), so warp-level barriers order the reads of
     // the two special logits, the in-place sweep and the corrections.
-    const int i = threadIdx.x / TPR, h = threadIdx.x % TPR;
+    const int i = map.row, h = map.slice;
     if constexpr (ROWPAR) g = rowc[i];
     const bool rvalid = g.valid > 0, inrange = g.valid >= 0;
     T* x = tile + (size_t)(inrange ? i : 0) * V;

@@ -193,6 +193,20 @@ template <int LPR, typename T> __device__ __forceinline__ T group_sum(T v) {
     for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// same with the group's lanes `stride` apart (stride 1: adjacent lanes, as above)
+template <int LPR, typename T> __device__ __forceinline__ T group_max_strided(T v, int stride) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        T w = __shfl_xor_sync(0xffffffffu, v, o * stride);
+        v = Real<T>::max(v, w);
+    }
+    return v;
+}
+template <int LPR, typename T> __device__ __forceinline__ T group_sum_strided(T v, int stride) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o * stride);
+    return v;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Lattice-space log-sum-exp.  The running alpha/beta values are kept in double (they reach

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -63,6 +64,31 @@ inline int read_set(EventSet& es, float* ms3) {
     return n;
 }
 
+// Dev aid, RNNT_B200_TIMELINE=1: timed events around every launch of the grouped (overlapped) schedule,
+// printed to stderr relative to the call's start.  Synchronises the call; never on in production.
+struct Timeline {
+    std::vector<std::pair<std::string, cudaEvent_t>> ev;
+    bool on = false;
+    void tick(const char* what, int k, cudaStream_t s) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.emplace_back(std::string(what) + std::to_string(k), e);
+    }
+    void dump() {
+        if (!on || ev.empty()) return;
+        cudaDeviceSynchronize();
+        for (auto& p : ev) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[0].second, p.second);
+            fprintf(stderr, "[timeline] %-14s %8.3f ms\n", p.first.c_str(), ms);
+        }
+        for (auto& p : ev) cudaEventDestroy(p.second);
+        ev.clear();
+    }
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Launch `kernel`; with pdl it may start while the previous kernel of the stream is still running (its
@@ -106,11 +132,12 @@ void func_attr_once(const void* kernel, cudaFuncAttribute attr, int value) {
 // utterances with the (bandwidth-bound) streaming passes of the others.  High priority so the
 // lattice CTAs are placed as soon as short-lived streaming CTAs retire.  Fork/join with events on
 // the caller's stream only, so the call stays capturable and stream-ordered for the caller.
-constexpr int kMaxGroups = 4;
+constexpr int kMaxGroups = 8;    // upper bound (RNNT_B200_GROUPS)
+constexpr int kAutoGroups = 4;   // what the overlap heuristic picks
 struct SidePool {
-    cudaStream_t stream[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t forked[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t joined[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream[kMaxGroups] = {};
+    cudaEvent_t forked[kMaxGroups] = {};
+    cudaEvent_t joined[kMaxGroups] = {};
     int device = -1;
     bool ok = false;
 };
@@ -314,6 +341,25 @@ inline int pick_tpr(int V) {
     while (tpr < 32 && V > 32 * tpr) tpr *= 2;
     return tpr;
 }
+// Shared-memory wavefronts of one warp-wide access of the chunk kernels' element walk under either
+// lane -> (row, slice) mapping (ChunkMap in rnnt_chunk.cuh).  A warp's access is served in phases of
+// 128 bytes' worth of lanes; within a phase lanes that fall on the same bank group serialise.
+inline int chunk_walk_cost(int V, int tpr, int elt, bool hmajor) {
+    const int unit = V % 2 == 0 ? 2 * elt : elt;   // bytes per lane access (pairs for even V)
+    const int per_phase = 128 / unit;
+    const int rpw = 32 / tpr;
+    int cost = 0;
+    for (int p0 = 0; p0 < 32; p0 += per_phase) {
+        int cnt[32] = {0}, worst = 0;
+        for (int l = p0; l < p0 + per_phase; ++l) {
+            const int il = hmajor ? l % rpw : l / tpr, h = hmajor ? l / rpw : l % tpr;
+            const long addr = (long)il * V * elt / unit + h;
+            worst = std::max(worst, ++cnt[addr % per_phase]);
+        }
+        cost += worst;
+    }
+    return cost;
+}
 inline bool chunk_enabled() {
     static const bool on = [] { const char* e = getenv("RNNT_B200_CHUNK"); return !(e && atoi(e) == 0); }();
     return on;
@@ -336,6 +382,9 @@ bool chunk_pass(const T* acts, T* grads, const int* labels, const int* xlen, con
     const unsigned grid = (unsigned)(((uint64_t)d.rows + rows_per - 1) / rows_per);
     const size_t smem = (size_t)rows_per * d.V * sizeof(T);
     const bool scaled = scale != T(1) || scale_vec;
+    static const int forced_map = [] { const char* e = getenv("RNNT_B200_CHUNK_MAP"); return e ? atoi(e) : -1; }();
+    int hmajor = chunk_walk_cost(d.V, tpr, (int)sizeof(T), true) < chunk_walk_cost(d.V, tpr, (int)sizeof(T), false);
+    if (forced_map == 0 || forced_map == 1) hmajor = forced_map;   // tuning hook
     // 8+ chunk CTAs per SM need most of the shared memory: ask for the largest carve-out once per kernel
     auto prefer_smem = [](auto kernel) {
         func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -347,15 +396,15 @@ bool chunk_pass(const T* acts, T* grads, const int* labels, const int* xlen, con
         if constexpr (NT / TPR >= 4) {
             if (pass == 1)
                 prefer_smem(rowstats_chunk_kernel<T, TPR, NT>)<<<grid, NT, smem, s>>>(
-                    acts, labels, xlen, ylen, static_cast<Pair*>(w.stat), static_cast<Fac*>(w.lp2), d);
+                    acts, labels, xlen, ylen, static_cast<Pair*>(w.stat), static_cast<Fac*>(w.lp2), d, hmajor);
             else if (scaled)
                 launch_k(prefer_smem(grad_chunk_kernel<T, TPR, NT, true>), dim3(grid), dim3(NT), smem, s, g_pdl, acts, grads,
                          labels, xlen, ylen, static_cast<const Pair*>(w.stat), static_cast<const Val*>(w.alphas),
-                         static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d);
+                         static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d, hmajor);
             else
                 launch_k(prefer_smem(grad_chunk_kernel<T, TPR, NT, false>), dim3(grid), dim3(NT), smem, s, g_pdl, acts, grads,
                          labels, xlen, ylen, static_cast<const Pair*>(w.stat), static_cast<const Val*>(w.alphas),
-                         static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d);
+                         static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d, hmajor);
         }
     };
     auto with_rpt = [&](auto tpr_c) {
@@ -490,8 +539,10 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         g.w = w;
         g.w.stat = static_cast<Pair*>(w.stat) + (size_t)b0 * cell_stride;
         g.w.lp2 = static_cast<char*>(w.lp2) + (size_t)b0 * lat_stride * 16;
-        g.w.alphas = static_cast<char*>(w.alphas) + (size_t)b0 * lat_stride * 8;
-        g.w.betas = static_cast<char*>(w.betas) + (size_t)b0 * lat_stride * 8;
+        // fp32 lattices are cell-major [b][t][u], fp64 ones diagonal-major (rnnt_kernels.cuh: cell / skew)
+        const size_t val_stride = sizeof(T) == 4 ? cell_stride : lat_stride;
+        g.w.alphas = static_cast<char*>(w.alphas) + (size_t)b0 * val_stride * 8;
+        g.w.betas = static_cast<char*>(w.betas) + (size_t)b0 * val_stride * 8;
         g.w.llf = static_cast<char*>(w.llf) + (size_t)b0 * 8;
         g.w.llb = static_cast<char*>(w.llb) + (size_t)b0 * 8;
         g.d = d;
@@ -507,13 +558,15 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         return g;
     };
     const bool with_beta = grads || want_beta;
+    bool co_running = false;   // set when the lattice of one group shares the GPU with the streaming passes of others
     auto launch_lattice = [&](const Group& g, cudaStream_t st) {
         const int threads = (opt.maxU + 31) / 32 * 32;
         dim3 grid(g.d.N, with_beta ? 2 : 1);
         if constexpr (sizeof(T) == 4) {
             // fp32: linear-domain wavefront with explicit exponents, COLS columns per lane (rnnt_lattice.cuh)
             const int lthreads = lattice_threads(opt.maxU);
-            const size_t ring = lattice_ring_bytes(opt.maxU);
+            const int depth = lattice_ring_depth(opt.maxU, co_running);
+            const size_t ring = lattice_ring_bytes(opt.maxU, depth);
             auto launch = [&](auto kernel, int static_smem) {
                 if (ring + static_smem > 48 * 1024)
                     func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
@@ -521,9 +574,11 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
                          static_cast<LogVal*>(g.w.alphas), static_cast<LogVal*>(g.w.betas), static_cast<LogVal*>(g.w.llf),
                          static_cast<LogVal*>(g.w.llb), g.costs, g.d);
             };
-            if (opt.maxU <= 32) launch(lattice_lin_kernel<1, false>, 64);
-            else if (opt.maxU <= 64) launch(lattice_lin_kernel<2, false>, 64);
-            else launch(lattice_lin_kernel<1, true>, kLinStaticSmem);
+            if (opt.maxU <= 32) launch(lattice_lin_kernel<1, false, 8>, 64);
+            else if (opt.maxU <= 64) launch(lattice_lin_kernel<2, false, 8>, 64);
+            else if (depth == 32) launch(lattice_lin_kernel<1, true, 32>, kLinStaticSmem);
+            else if (depth == 16) launch(lattice_lin_kernel<1, true, 16>, kLinStaticSmem);
+            else launch(lattice_lin_kernel<1, true, 8>, kLinStaticSmem);
         } else {
             // fp64: log-domain wavefront (rnnt_kernels.cuh)
             const size_t ring = (size_t)kRing * threads * sizeof(double2);
@@ -549,12 +604,12 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
     // lattice CTAs slow the streaming kernels a little, so the gain is modest, and there is none
     // when no pass 2 follows in the same call (loss-only / operator forward) - those stay in order.
     int groups = 1;
-    if (phase == kFull && grads && N >= 2 * kMaxGroups && !d.tmajor) {
+    if (phase == kFull && grads && N >= 2 * kAutoGroups && !d.tmajor) {
         static const int forced = [] { const char* e = getenv("RNNT_B200_GROUPS"); return e ? atoi(e) : 0; }();
         const double lattice_us = 0.25 * (opt.maxT + opt.maxU) + 20.0;
         const double stream_us = (double)rows64 * V * sizeof(IO) * (grads ? 3.0 : 1.0) / 6.9e6;
-        if (stream_us > 400.0 && lattice_us > 0.08 * stream_us) groups = kMaxGroups;
-        if (forced >= 1 && forced <= kMaxGroups) groups = forced;
+        if (stream_us > 400.0 && lattice_us > 0.08 * stream_us) groups = kAutoGroups;
+        if (forced >= 1 && forced <= kMaxGroups && forced <= N) groups = forced;
         if (groups > 1 && !side_pool().ok) groups = 1;
     }
 
@@ -587,7 +642,12 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         }
     } else {
         SidePool& pool = side_pool();
+        co_running = true;
         bool fork_ok = true;   // a failed fork/join would leave the gradient pass unordered against a lattice
+        static const bool tl_env = [] { const char* e = getenv("RNNT_B200_TIMELINE"); return e && atoi(e) != 0; }();
+        Timeline tl;
+        tl.on = tl_env;
+        tl.tick("start", 0, s);
         Group gs[kMaxGroups];
         for (int k = 0; k < groups; ++k) {
             const int b0 = (int)((int64_t)N * k / groups), b1 = (int)((int64_t)N * (k + 1) / groups);
@@ -597,9 +657,12 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         for (int k = 0; k < groups; ++k) {
             stream_pass<T, IO>(gs[k].acts, nullptr, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w, scale,
                                gs[k].scale_vec, gs[k].d, s, 1);
+            tl.tick("rowstats_end", k, s);
             fork_ok &= cudaEventRecord(pool.forked[k], s) == cudaSuccess;
             fork_ok &= cudaStreamWaitEvent(pool.stream[k], pool.forked[k], 0) == cudaSuccess;
+            tl.tick("lattice_beg", k, pool.stream[k]);
             launch_lattice(gs[k], pool.stream[k]);
+            tl.tick("lattice_end", k, pool.stream[k]);
             fork_ok &= cudaEventRecord(pool.joined[k], pool.stream[k]) == cudaSuccess;
         }
         mark(1, s);
@@ -607,10 +670,13 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
         for (int k = 0; k < groups; ++k) {
             fork_ok &= cudaStreamWaitEvent(s, pool.joined[k], 0) == cudaSuccess;
             if (k == 0) mark(2, s);
+            tl.tick("grad_beg", k, s);
             if (grads && phase != kForward)
                 stream_pass<T, IO>(gs[k].acts, gs[k].grads, gs[k].labels, gs[k].xlen, gs[k].ylen, gs[k].w,
                                    scale, gs[k].scale_vec, gs[k].d, s, 2);
+            tl.tick("grad_end", k, s);
         }
+        tl.dump();
         if (grads && phase != kForward) mark(3, s);
         if (!fork_ok) {
             cudaStreamSynchronize(s);
@@ -765,15 +831,15 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     {
         dim3 grid(N, with_beta ? 2 : 1);
         const int lthreads = lattice_threads(U);
-        const size_t ring = lattice_ring_bytes(U);
+        const size_t ring = lattice_ring_bytes(U, 8);
         auto launch = [&](auto kernel, int static_smem) {
             if (ring + static_smem > 48 * 1024)
                 func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
             kernel<<<grid, lthreads, ring, s>>>(w.lp2, xlen, ylen, w.alphas, w.betas, w.llf, w.llb, costs, d);
         };
-        if (U <= 32) launch(lattice_lin_kernel<1, false>, 64);
-        else if (U <= 64) launch(lattice_lin_kernel<2, false>, 64);
-        else launch(lattice_lin_kernel<1, true>, kLinStaticSmem);
+        if (U <= 32) launch(lattice_lin_kernel<1, false, 8>, 64);
+        else if (U <= 64) launch(lattice_lin_kernel<2, false, 8>, 64);
+        else launch(lattice_lin_kernel<1, true, 8>, kLinStaticSmem);
     }
     g_last_launches += 5;
     }  // phase != kBackward

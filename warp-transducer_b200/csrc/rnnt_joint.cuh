@@ -223,9 +223,9 @@ joint_weights_kernel(const float4* __restrict__ lp2, const LogVal* __restrict__ 
     float w = 0.0f, bk = 0.0f, lb = 0.0f;
     const float scale = scale_vec ? scale_in * __ldg(scale_vec + b) : scale_in;
     if ((int)t < Tb && (int)u < Ub) {
-        const size_t q = skew(d, b, t, u);
         // everything in the exp2 domain: log2 occupancy = exact integer part + small float part
-        const float4 fc = lp2[q];
+        const float4 fc = lp2[skew(d, b, t, u)];
+        const size_t q = cell(d, b, t, u);
         const LogVal a = alphas[q], ll = llf[b], bq = betas[q];
         const int oe = a.e - ll.e;
         const float ol = a.l - ll.l;
@@ -238,7 +238,7 @@ joint_weights_kernel(const float4* __restrict__ lp2, const LogVal* __restrict__ 
             bk = scale * exp2f((float)oe + ol + lpb2);
         }
         if ((int)u < Ub - 1) {
-            const LogVal bn = betas[q + d.maxU + 1];
+            const LogVal bn = betas[q + 1];
             const float lpl2 = (float)__float_as_int(fc.w) + log2f(fc.z);
             lb = scale * exp2f((float)(oe + bn.e) + (ol + bn.l) + lpl2);
         }

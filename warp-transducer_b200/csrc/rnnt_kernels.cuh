@@ -49,6 +49,15 @@ __host__ __device__ __forceinline__ size_t lattice_block(const Dims& d) {
 __device__ __forceinline__ size_t skew(const Dims& d, uint32_t b, uint32_t t, uint32_t u) {
     return (size_t)b * lattice_block(d) + (size_t)(t + u) * d.maxU + u;
 }
+// fp32 path: the transition factors (lp2) stay diagonal-major - the wavefront prefetches them a ring of
+// diagonals ahead with one 16-byte copy per lane - but ALPHA and BETA are stored CELL-MAJOR [b][t][u],
+// (t+1,u) at +maxU, (t,u+1) at +1: the consumer is pass 2, whose rows arrive in (b,t,u) order, so a warp's
+// fetch of its rows' lattice values is one or two cache lines instead of one line per row (ncu, round 2:
+// those scattered loads - not the element sweep - held the short-row gradient kernel's memory pipe).
+// The wavefront pays with a strided 8-byte store per step, off its dependent chain.
+__device__ __forceinline__ size_t cell(const Dims& d, uint32_t b, uint32_t t, uint32_t u) {
+    return ((size_t)b * d.maxT + t) * d.maxU + u;
+}
 
 // clamp the per-utterance extents into the tensor so corrupt lengths cannot index outside it
 __device__ __forceinline__ void utt_extent(const Dims& d, const int* __restrict__ xlen,
@@ -492,7 +501,7 @@ __device__ __forceinline__ RowGrad<float> row_grad_setup(const Dims& d, uint32_t
     using R = Real<float>;
     RowGrad<float> g;
     const float2 st = __ldg(stat + r);
-    const size_t q = skew(d, b, t, u);
+    const size_t q = cell(d, b, t, u);   // (t+1,u) at q + maxU, (t,u+1) at q + 1
     const LogVal a = alphas[q], ll = llf[b], bq = betas[q];
     const int oe = a.e - ll.e;            // occupancy exponent alpha - ll (exact)
     const float ol = a.l - ll.l - st.y * R::kLog2e;
@@ -508,7 +517,7 @@ __device__ __forceinline__ RowGrad<float> row_grad_setup(const Dims& d, uint32_t
     }
     g.y = -1;
     if ((int)u < Ub - 1) {
-        const LogVal bn = betas[q + d.maxU + 1];
+        const LogVal bn = betas[q + 1];
         g.cL = (float)(oe + bn.e) + (ol + bn.l);
         g.y = __ldg(labels + (size_t)b * (d.maxU - 1) + u);
     }
@@ -516,7 +525,7 @@ __device__ __forceinline__ RowGrad<float> row_grad_setup(const Dims& d, uint32_t
 }
 // Same constants with every load issued unconditionally and at once (short rows: the row's scalars are
 // the critical path of a chunk CTA, two dependent rounds of loads cost ~1 us).  Reads are in bounds for
-// every (t,u) of the tensor: q + maxU + 1 stays inside the lattice arrays plus the slack carve() leaves.
+// every (t,u) of the tensor: q + maxU stays inside the lattice arrays plus the slack carve() leaves.
 __device__ __forceinline__ RowGrad<float> row_grad_setup_spec(const Dims& d, uint32_t r, uint32_t b, uint32_t t,
                                                               uint32_t u, const int* __restrict__ xlen,
                                                               const int* __restrict__ ylen,
@@ -526,10 +535,10 @@ __device__ __forceinline__ RowGrad<float> row_grad_setup_spec(const Dims& d, uin
                                                               const LogVal* __restrict__ betas,
                                                               const LogVal* __restrict__ llf, int& Tb, int& Ub) {
     using R = Real<float>;
-    const size_t q = skew(d, b, t, u);
+    const size_t q = cell(d, b, t, u);
     const int xl = __ldg(xlen + b), yl = __ldg(ylen + b);
     const float2 st = __ldg(stat + r);
-    const LogVal a = alphas[q], ll = llf[b], bq = betas[q], bt = betas[q + d.maxU], bu = betas[q + d.maxU + 1];
+    const LogVal a = alphas[q], ll = llf[b], bq = betas[q], bt = betas[q + d.maxU], bu = betas[q + 1];
     const int lab = (int)u < d.maxU - 1 ? __ldg(labels + (size_t)b * (d.maxU - 1) + u) : 0;
     Tb = min(max(xl, 1), d.maxT);
     Ub = min(max(yl + 1, 1), d.maxU);

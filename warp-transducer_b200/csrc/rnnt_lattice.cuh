@@ -40,7 +40,7 @@ __device__ __forceinline__ void lin_add(float v1, int e1, float v2, int e2, floa
     e = max(E + (bits >> 23) - 127, kEZero);
     v = __int_as_float((bits & 0x007fffff) | 0x3f800000);
 }
-constexpr int kLinRing = 8;    // diagonals of factors in flight per thread (the step loop is unrolled by this)
+constexpr int kLinRing = 8;    // the step loop is unrolled by this; the factor ring holds RD = 8, 16 or 32 diagonals per thread
 constexpr int kEdge = 16;      // slots of the cross-warp exchange ring (multiple of kLinRing, power of two)
 constexpr int kEdgeWarps = 32;
 constexpr int kLinStaticSmem = kEdgeWarps * kEdge * 16 + kEdgeWarps * 4 + 16;
@@ -92,13 +92,16 @@ __device__ __forceinline__ void sts_volatile(uint32_t addr, int v) {
 // lane 33..64 labels are a single warp with no cross-warp exchange at all.
 // (See lattice_cols() for when that pays and when it does not.)
 // =================================================================================================
-template <int COLS, bool MULTI, bool BACKWARD>
+template <int COLS, bool MULTI, bool BACKWARD, int RD>
 __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac, const int* __restrict__ xlen,
                                                  const int* __restrict__ ylen, LogVal* __restrict__ out,
                                                  LogVal* __restrict__ llout, float* __restrict__ costs,
                                                  const Dims& d, uint32_t ring_base, uint32_t edge_base,
-                                                 uint32_t prog_base, int* bad_any) {
+                                                 uint32_t prog_base, uint32_t delay_base, int* bad_any) {
     constexpr int DIR = BACKWARD ? -1 : 1;
+    static_assert(RD % kLinRing == 0 && RD >= kLinRing, "ring depth: a multiple of the unroll factor");
+    static_assert(!(MULTI && COLS > 1), "the store delay line below is written for one column per lane");
+    static_assert(kLinRing == 8, "delay line depth = unroll factor = 8");
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int NT = blockDim.x;
@@ -124,7 +127,17 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
     const int dstep = DIR * mU;                          // pointer step per diagonal in step order
     const int n0 = BACKWARD ? last : 0;
     const float4* gp = fac + base + u0 + (ptrdiff_t)n0 * mU;  // column u0's record of the next diagonal to fetch
-    LogVal* sp = out + base + u0 + (ptrdiff_t)n0 * mU;
+    // lattice values go out CELL-MAJOR (see cell() in rnnt_kernels.cuh): cell (n-u, u) = n*mU - u*(mU-1)
+    ptrdiff_t si = (ptrdiff_t)b * d.maxT * mU + (ptrdiff_t)n0 * mU - (ptrdiff_t)u0 * (mU - 1);
+    // Multi-warp wavefronts: a step's 32 cells of a warp lie in 32 different rows t - written directly, every
+    // warp-store is 32 sectors, and ten warps of one CTA saturate the SM's store path (measured: 0.40 -> 0.69 ms
+    // at U = 301).  Each lane therefore DELAYS its store by kd steps through a private 8-deep line in shared
+    // memory, kd = 7 - u%8 (alpha) / u%8 (beta): the 8 lanes of a group then store the same row t at the same
+    // step - 64 contiguous bytes per group, 2-3 sectors instead of 8.
+    const int kd = MULTI ? (BACKWARD ? (u0 & 7) : 7 - (u0 & 7)) : 0;
+    const uint32_t delay_u = delay_base + (uint32_t)(tid >> 5) * 2048u + (uint32_t)lane * 8u;   // [8][32] x 8 B per warp
+    const int kdn = (8 - kd) & 7;        // row of step s - kd  =  (s + kdn) & 7
+    si -= (ptrdiff_t)kd * DIR * mU;
     int nu = n0 - u0;                                    // (current diagonal) - u0
     // Ring slots that no copy will fill hold NEUTRAL factors {1, 0, 1, log zero}: the step body below runs
     // unconditionally - a column that is not active yet keeps its "log zero" unchanged (and beta's virtual
@@ -134,19 +147,20 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %1, %3};" ::"r"(addr), "r"(0x3f800000), "r"(0), "r"(kEZero) : "memory");
     };
 #pragma unroll
-    for (int k = 0; k < kLinRing; ++k) {
+    for (int k = 0; k < RD; ++k) {
 #pragma unroll
         for (int c = 0; c < COLS; ++c) {
             const bool act = (unsigned)(nu - c + k * DIR) < width[c];
             const uint32_t slot = ring_u + k * step_bytes + c * 16;
-            if (k < kLinRing - 1 && act) cp_async16_s(slot, gp + c);
-            else if (k < kLinRing - 1 || !act) neutral(slot);   // (the last slot is step 0's refill target)
+            if (k < RD - 1 && act) cp_async16_s(slot, gp + c);
+            else if (k < RD - 1 || !act) neutral(slot);   // (the last slot is step 0's refill target)
         }
-        if (k < kLinRing - 1) {
+        if (k < RD - 1) {
             cp_async_commit();
             gp += dstep;
         }
     }
+    uint32_t roff = 0;   // byte offset of the ring slot of step s0 (always 0 when the ring is one unroll group deep)
     // running values.  alpha: (sv,se) = alpha(t,u) p_blank(t,u) offered to (t+1,u), (ov,oe) = alpha(t,u)
     // p_label(t,u) offered to (t,u+1).  beta: (sv,se) = beta(t+1,u).
     float sv[COLS], ov[COLS];
@@ -182,17 +196,20 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
         for (int j = 0; j < kLinRing; ++j) {
             const int s = s0 + j;
             if (s > last) break;
-            cp_async_wait<kLinRing - 2>();   // this thread's factors of the current diagonal have landed
+            cp_async_wait<RD - 2>();   // this thread's factors of the current diagonal have landed
             // refill the slot of the previous step (private to this thread, already consumed)
+            uint32_t prev;
+            if (RD == kLinRing) prev = ring_u + ((j + kLinRing - 1) % kLinRing) * step_bytes;
+            else if (j > 0) prev = ring_u + roff + (j - 1) * step_bytes;
+            else prev = ring_u + (roff == 0 ? RD * step_bytes : roff) - step_bytes;
 #pragma unroll
             for (int c = 0; c < COLS; ++c)
-                if ((unsigned)(nu - c + (kLinRing - 1) * DIR) < width[c])
-                    cp_async16_s(ring_u + ((j + kLinRing - 1) % kLinRing) * step_bytes + c * 16, gp + c);
+                if ((unsigned)(nu - c + (RD - 1) * DIR) < width[c]) cp_async16_s(prev + c * 16, gp + c);
             cp_async_commit();
             gp += dstep;
             float4 f[COLS];   // neutral / stale factors where a column is not active
 #pragma unroll
-            for (int c = 0; c < COLS; ++c) f[c] = lds128(ring_u + j * step_bytes + c * 16);
+            for (int c = 0; c < COLS; ++c) f[c] = lds128(ring_u + (RD == kLinRing ? 0u : roff) + j * step_bytes + c * 16);
 
             // the one neighbour value that crosses lanes, from the previous step
             float nv;
@@ -244,9 +261,21 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
 #pragma unroll
             for (int c = 0; c < COLS; ++c) {
                 nansum = fmaf(f[c].x, f[c].z, nansum);
-                if ((unsigned)(nu - c) < width[c]) sp[c] = to_logval(v[c], e[c]);
+                if (!MULTI) {
+                    if ((unsigned)(nu - c) < width[c]) out[si - c * (mU - 1)] = to_logval(v[c], e[c]);
+                } else {
+                    const LogVal now = to_logval(v[c], e[c]);
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(delay_u + (uint32_t)(j & 7) * 256u), "r"(now.e),
+                                 "r"(__float_as_int(now.l)) : "memory");
+                    LogVal old;
+                    int ol;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(old.e), "=r"(ol)
+                                 : "r"(delay_u + (uint32_t)((j + kdn) & 7) * 256u) : "memory");
+                    old.l = __int_as_float(ol);
+                    if ((unsigned)(nu - kd * DIR) < width[c]) out[si] = old;   // the value of kd steps ago
+                }
             }
-            sp += dstep;
+            si += dstep;
             nu += DIR;
             if (MULTI) {
                 const uint32_t slot_off = (eoff + (uint32_t)j * 16) & (kEdge * 16 - 1);
@@ -259,8 +288,25 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
                 }
             }
         }
+        if (RD != kLinRing) {
+            roff += kLinRing * step_bytes;
+            if (roff == RD * step_bytes) roff = 0;
+        }
     }
     cp_async_wait<0>();
+    if (MULTI) {
+        // drain the delay lines: the values of the last kd steps are still to be stored
+        for (int s = last + 1; s <= last + 7; ++s) {
+            LogVal old;
+            int ol;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(old.e), "=r"(ol)
+                         : "r"(delay_u + (uint32_t)((s + kdn) & 7) * 256u) : "memory");
+            old.l = __int_as_float(ol);
+            if (s - kd <= last && (unsigned)(nu - kd * DIR) < width[0]) out[si] = old;
+            si += dstep;
+            nu += DIR;
+        }
+    }
 
     // NaN anywhere in this utterance's factors -> NaN cost (the reference propagates it through log_plus)
     bool bad = nansum != nansum;
@@ -296,12 +342,12 @@ __device__ __forceinline__ void lattice_lin_body(const float4* __restrict__ fac,
     }
 }
 
-template <int COLS, bool MULTI>
+template <int COLS, bool MULTI, int RD>
 __global__ void __launch_bounds__(MULTI ? 1024 / COLS : 32)
 lattice_lin_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen, const int* __restrict__ ylen,
                    LogVal* __restrict__ alphas, LogVal* __restrict__ betas, LogVal* __restrict__ llf,
                    LogVal* __restrict__ llb, float* __restrict__ costs, const Dims d) {
-    extern __shared__ __align__(16) unsigned char ring_raw[];   // [kLinRing][blockDim.x][COLS] float4, thread-private
+    extern __shared__ __align__(16) unsigned char ring_raw[];   // [RD][blockDim.x][COLS] float4, thread-private
     __shared__ __align__(16) int4 edge[MULTI ? kEdgeWarps * kEdge : 1];
     __shared__ int prog[MULTI ? kEdgeWarps : 1];
     __shared__ int bad_any;
@@ -313,12 +359,13 @@ lattice_lin_kernel(const float4* __restrict__ fac, const int* __restrict__ xlen,
         __syncthreads();
     }
     const uint32_t ring_base = smem_u32(ring_raw), edge_base = smem_u32(edge), prog_base = smem_u32(prog);
+    const uint32_t delay_base = ring_base + (uint32_t)RD * blockDim.x * COLS * 16u;   // MULTI only: [warps][8][32] x 8 B
     pdl_trigger();   // the gradient kernel may launch and read the logits while the wavefront runs
     pdl_wait();      // pass 1's factors are complete and visible
     if (blockIdx.y == 0)
-        lattice_lin_body<COLS, MULTI, false>(fac, xlen, ylen, alphas, llf, costs, d, ring_base, edge_base, prog_base, &bad_any);
+        lattice_lin_body<COLS, MULTI, false, RD>(fac, xlen, ylen, alphas, llf, costs, d, ring_base, edge_base, prog_base, delay_base, &bad_any);
     else
-        lattice_lin_body<COLS, MULTI, true>(fac, xlen, ylen, betas, llb, costs, d, ring_base, edge_base, prog_base, &bad_any);
+        lattice_lin_body<COLS, MULTI, true, RD>(fac, xlen, ylen, betas, llb, costs, d, ring_base, edge_base, prog_base, delay_base, &bad_any);
 }
 
 // Columns per lane for a label extent.  Measured on B200: a lone warp issues one instruction every 3-4
@@ -331,6 +378,24 @@ inline int lattice_threads(int maxU) {
     const int per_warp = 32 * lattice_cols(maxU);
     return (maxU + per_warp - 1) / per_warp * 32;
 }
-inline size_t lattice_ring_bytes(int maxU) { return (size_t)kLinRing * lattice_threads(maxU) * lattice_cols(maxU) * 16; }
+// Diagonals of factors each thread keeps in flight.  8 covers the DRAM latency of an otherwise idle GPU
+// (8 steps x ~220 ns); next to the streaming passes of other batch groups the loaded latency is several
+// microseconds and the multi-warp wavefront starves, so there the ring is as deep as ~100 KB allow.
+// RNNT_B200_LAT_RING = 8 | 16 | 32 forces it (tuning hook).
+inline int lattice_ring_depth(int maxU, bool co_running) {
+    if (maxU <= 64) return 8;
+    static const int forced = [] { const char* e = getenv("RNNT_B200_LAT_RING"); return e ? atoi(e) : 0; }();
+    const size_t per_slot = (size_t)lattice_threads(maxU) * lattice_cols(maxU) * 16;
+    int depth = 8;
+    if (co_running)
+        while (depth < 32 && per_slot * depth * 2 <= 100 * 1024) depth *= 2;
+    if ((forced == 8 || forced == 16 || forced == 32) && per_slot * forced + kLinStaticSmem <= 200 * 1024) depth = forced;
+    return depth;
+}
+// dynamic shared memory: the factor ring, plus (multi-warp kernels) one 2 KB store delay line per warp
+inline size_t lattice_ring_bytes(int maxU, int depth) {
+    const size_t threads = lattice_threads(maxU);
+    return (size_t)depth * threads * lattice_cols(maxU) * 16 + (maxU > 64 ? threads * 64 : 0);
+}
 
 }  // namespace b200rnnt
