@@ -177,6 +177,40 @@ template <typename T, typename IO> __device__ __forceinline__ T ld_scalar(const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// 16-bit storage, two elements per 32-bit word: maximum on the packed word (HMNMX2 - one instruction
+// per two elements, no conversion) and conversion of a word to two floats (bf16: a shift and a mask).
+// ---------------------------------------------------------------------------------------------
+template <typename IO> struct Packed16;
+template <> struct Packed16<__nv_bfloat16> {
+    static constexpr unsigned kNegInf2 = 0xFF80FF80u;
+    static __device__ __forceinline__ unsigned max2(unsigned a, unsigned b) {
+        union { unsigned u; __nv_bfloat162 h; } x, y, z;
+        x.u = a, y.u = b;
+        z.h = __hmax2(x.h, y.h);
+        return z.u;
+    }
+    static __device__ __forceinline__ void to_floats(unsigned w, float& lo, float& hi) {
+        lo = __uint_as_float(w << 16);
+        hi = __uint_as_float(w & 0xffff0000u);
+    }
+};
+template <> struct Packed16<__half> {
+    static constexpr unsigned kNegInf2 = 0xFC00FC00u;
+    static __device__ __forceinline__ unsigned max2(unsigned a, unsigned b) {
+        union { unsigned u; __half2 h; } x, y, z;
+        x.u = a, y.u = b;
+        z.h = __hmax2(x.h, y.h);
+        return z.u;
+    }
+    static __device__ __forceinline__ void to_floats(unsigned w, float& lo, float& hi) {
+        union { unsigned u; __half2 h; } x;
+        x.u = w;
+        const float2 f = __half22float2(x.h);
+        lo = f.x, hi = f.y;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Reductions over an aligned group of LPR lanes (LPR a power of two <= 32) by xor-shuffle.
 // Every lane of the warp must call these (full mask).
 // ---------------------------------------------------------------------------------------------

@@ -883,8 +883,8 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
                 joint_gemm_kernel<EpiGrad><<<grid, 256, 0, s>>>(A, B, U, V, T, 1, EpiGrad{w.eg, dG, U, V});
             }
         }
-        joint_sparse_f_kernel<<<(N * T + 127) / 128, 128, 0, s>>>(dF, w.bk, w.lb, labels, ylen, jd);
-        joint_sparse_g_kernel<<<(N * U + 127) / 128, 128, 0, s>>>(dG, w.bk, w.lb, labels, xlen, ylen, jd);
+        joint_sparse_f_kernel<<<(N * T + 3) / 4, 128, 0, s>>>(dF, w.bk, w.lb, labels, ylen, jd);
+        joint_sparse_g_kernel<<<(N * U + 3) / 4, 128, 0, s>>>(dG, w.bk, w.lb, labels, xlen, ylen, jd);
         g_last_launches += 5;
     }
     return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;

@@ -307,12 +307,34 @@ struct EpiGrad {
 };
 
 // ---- J6: the blank / label terms (sparse in k) -------------------------------------------------------
-// one thread per (b,t) for dF and per (b,u) for dG; sequential over the short other axis so repeated
-// labels accumulate without atomics.
+// One WARP per (b,t) row of dF and per (b,u) row of dG.  The blank term is a warp sum; the label terms are
+// one read-modify-write per distinct label: lanes holding the same label are found with a warp match, the
+// lowest of them adds the group's values in lane order (deterministic, no atomics) and updates the row.
+// Chunks of 32 labels are processed in order with a warp barrier between them.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// row[key] -= sum of val over the lanes with this key (lanes with key < 0 hold nothing); whole warp calls
+__device__ __forceinline__ void warp_scatter_sub(float* row, int key, float val) {
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    float acc = 0.0f;
+    // every lane walks its own peer set in lane order; shuffles are executed by the whole warp
+    for (int src = 0; src < 32; ++src) {
+        const float v = __shfl_sync(0xffffffffu, val, src);
+        if ((peers >> src) & 1u) acc += v;
+    }
+    if (key >= 0 && lane == leader) row[key] -= acc;
+}
+
 __global__ void __launch_bounds__(128)
 joint_sparse_f_kernel(float* __restrict__ dF, const float* __restrict__ Bk, const float* __restrict__ Lb,
                       const int* __restrict__ labels, const int* __restrict__ ylen, const JointDims jd) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (b,t)
+    const int lane = threadIdx.x & 31;
     if (i >= jd.N * jd.T) return;
     const int b = i / jd.T;
     const int Ub = min(max(__ldg(ylen + b) + 1, 1), jd.U);
@@ -320,16 +342,23 @@ joint_sparse_f_kernel(float* __restrict__ dF, const float* __restrict__ Bk, cons
     const float* bk = Bk + (size_t)i * jd.U;
     const float* lb = Lb + (size_t)i * jd.U;
     float sb = 0.0f;
-    for (int u = 0; u < Ub; ++u) sb += bk[u];
-    row[jd.blank] -= sb;
-    for (int u = 0; u < Ub - 1; ++u) row[__ldg(labels + (size_t)b * (jd.U - 1) + u)] -= lb[u];
+    for (int u = lane; u < Ub; u += 32) sb += bk[u];
+    sb = warp_sum(sb);
+    if (lane == 0) row[jd.blank] -= sb;
+    for (int u0 = 0; u0 < Ub - 1; u0 += 32) {
+        __syncwarp();
+        const int u = u0 + lane;
+        const bool has = u < Ub - 1;
+        warp_scatter_sub(row, has ? __ldg(labels + (size_t)b * (jd.U - 1) + u) : -1, has ? lb[u] : 0.0f);
+    }
 }
 
 __global__ void __launch_bounds__(128)
 joint_sparse_g_kernel(float* __restrict__ dG, const float* __restrict__ Bk, const float* __restrict__ Lb,
                       const int* __restrict__ labels, const int* __restrict__ xlen,
                       const int* __restrict__ ylen, const JointDims jd) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (b,u)
+    const int lane = threadIdx.x & 31;
     if (i >= jd.N * jd.U) return;
     const int b = i / jd.U, u = i % jd.U;
     const int Tb = min(max(__ldg(xlen + b), 1), jd.T);
@@ -337,13 +366,17 @@ joint_sparse_g_kernel(float* __restrict__ dG, const float* __restrict__ Bk, cons
     if (u >= Ub) return;
     float* row = dG + (size_t)i * jd.V;
     float sb = 0.0f, sl = 0.0f;
-    for (int t = 0; t < Tb; ++t) {
+    for (int t = lane; t < Tb; t += 32) {
         const size_t c = ((size_t)b * jd.T + t) * jd.U + u;
         sb += Bk[c];
         sl += Lb[c];
     }
-    row[jd.blank] -= sb;
-    if (u < Ub - 1) row[__ldg(labels + (size_t)b * (jd.U - 1) + u)] -= sl;
+    sb = warp_sum(sb);
+    sl = warp_sum(sl);
+    if (lane == 0) {
+        row[jd.blank] -= sb;
+        if (u < Ub - 1) row[__ldg(labels + (size_t)b * (jd.U - 1) + u)] -= sl;
+    }
 }
 
 }  // namespace b200rnnt
