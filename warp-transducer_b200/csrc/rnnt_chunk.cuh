@@ -36,15 +36,25 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Every waiting thread is SUSPENDED by the hardware for up to the hint (ns) per probe instead of
-// spinning: a CTA that waits for its chunk costs the SM no issue slots (pass 1 is issue-bound).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Waiting threads SLEEP between probes (ns > 0: try_wait with a suspend-time hint, which compiles to
+// SYNCS.TRYWAIT + NANOSLEEP ns) instead of spinning, so a CTA that waits for its chunk costs the SM no issue
+// slots (pass 1 is issue-bound).  The sleep is a quantum, not an upper bound - a wait is rounded up to whole
+// quanta - so it is a tuned value (RNNT_B200_CHUNK_WAIT_NS); ns = 0 spins on test_wait.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t ns) {
     uint32_t done = 0;
+    if (ns == 0) {
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done)
+                         : "r"(bar), "r"(parity)
+                         : "memory");
+        return;
+    }
     while (!done) {
         asm volatile(
             "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(2000u)
+            : "r"(bar), "r"(parity), "r"(ns)
             : "memory");
     }
 }
@@ -104,7 +114,7 @@ template <typename T, int TPR, int NT>
 __global__ void __launch_bounds__(NT)
 rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels, const int* __restrict__ xlen,
                       const int* __restrict__ ylen, typename Real<T>::pair* __restrict__ stat,
-                      typename Lat<T>::fac* __restrict__ lp2, const Dims d, const int hmajor) {
+                      typename Lat<T>::fac* __restrict__ lp2, const Dims d, const int hmajor, const uint32_t wait_ns) {
     using R = Real<T>;
     using Pair = typename R::pair;
     constexpr int ROWS = NT / TPR;
@@ -139,11 +149,11 @@ rowstats_chunk_kernel(const T* __restrict__ acts, const int* __restrict__ labels
     // real cell (a fully padded chunk - ragged batches only - costs one wasted read, nothing else)
     const bool any_valid = __syncthreads_or(valid);
     if (!any_valid) {
-        if (bulk && threadIdx.x == 0) mbar_wait(bar, 0);   // shared memory must outlive the in-flight copy
+        if (bulk && threadIdx.x == 0) mbar_wait(bar, 0, wait_ns);   // shared memory must outlive the in-flight copy
         return;
     }
     if (bulk) {
-        mbar_wait(bar, 0);
+        mbar_wait(bar, 0, wait_ns);
     } else {
         const T* src = acts + (uint64_t)r0 * V;
         for (uint32_t k = threadIdx.x; k < nrows * (uint32_t)V; k += NT) tile[k] = ld_scalar<T>(src + k);
@@ -226,7 +236,7 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
                   const int* __restrict__ xlen, const int* __restrict__ ylen,
                   const typename Real<T>::pair* __restrict__ stat, const typename Lat<T>::val* __restrict__ alphas,
                   const typename Lat<T>::val* __restrict__ betas, const typename Lat<T>::val* __restrict__ llf, const T scale_in,
-                  const T* __restrict__ scale_vec, const Dims d, const int hmajor) {
+                  const T* __restrict__ scale_vec, const Dims d, const int hmajor, const uint32_t wait_ns) {
     using R = Real<T>;
     using Pair = typename R::pair;
     constexpr int ROWS = NT / TPR;
@@ -305,14 +315,14 @@ grad_chunk_kernel(const T* __restrict__ acts, T* __restrict__ grads, const int* 
 #pragma unroll
             for (int c = 0; c < VEC; ++c) z.v[c] = 0;
             for (uint32_t k = threadIdx.x; k < nelem / VEC; k += NT) st_stream<T, VEC>(gout + (size_t)k * VEC, z);
-            if (threadIdx.x == 0) mbar_wait(bar, 0);   // shared memory must outlive the in-flight copy
+            if (threadIdx.x == 0) mbar_wait(bar, 0, wait_ns);   // shared memory must outlive the in-flight copy
         } else {
             for (uint32_t k = threadIdx.x; k < nelem; k += NT) gout[k] = T(0);
         }
         return;
     }
     if (bulk) {
-        mbar_wait(bar, 0);
+        mbar_wait(bar, 0, wait_ns);
     } else {
         const T* src = acts + (uint64_t)r0 * V;
         for (uint32_t k = threadIdx.x; k < nelem; k += NT) tile[k] = ld_scalar<T>(src + k);

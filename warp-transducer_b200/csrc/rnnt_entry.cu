@@ -333,12 +333,15 @@ void stream_passes(const IO* acts, IO* grads, const int* labels, const int* xlen
 }
 
 // ---- short rows (<= 512 B): chunk kernels (rnnt_chunk.cuh), TMA bulk staging of R consecutive rows ----
-// threads per row = the power of two dividing V (bank-conflict-free interleaved walk), raised until a
-// thread owns at most 32 elements.  RNNT_B200_CHUNK=0 routes short rows to the register-tile kernels.
+// Threads per row: as FEW as keep a thread's share at <= 32 elements (two for even V, so that the walk can use
+// 8-byte pairs) - every lane of a row repeats the row's fixed work (mapping, shuffles, reductions), and at
+// V = 28 that fixed work dominated: 4 lanes/row 0.099 ms, 2 lanes/row 0.079 ms for the whole C2 call.  Bank
+// conflicts are dealt with by the lane mapping (chunk_walk_cost), not by the lane count.
+// RNNT_B200_CHUNK=0 routes short rows to the register-tile kernels.
 inline int pick_tpr(int V) {
     int tpr = 1;
-    while (tpr < 32 && V % (tpr * 2) == 0) tpr *= 2;
     while (tpr < 32 && V > 32 * tpr) tpr *= 2;
+    if (tpr == 1 && V % 2 == 0 && V > 16) tpr = 2;
     return tpr;
 }
 // Shared-memory wavefronts of one warp-wide access of the chunk kernels' element walk under either
@@ -376,12 +379,15 @@ bool chunk_pass(const T* acts, T* grads, const int* labels, const int* xlen, con
     static const int forced_nt = [] { const char* e = getenv("RNNT_B200_CHUNK_NT"); return e ? atoi(e) : 0; }();
     int nt = sizeof(T) >= 8 ? 128 : 256;
     if (sizeof(T) == 4 && (forced_nt == 64 || forced_nt == 128 || forced_nt == 256)) nt = forced_nt;
-    const int tpr = pick_tpr(d.V);
+    static const int forced_tpr = [] { const char* e = getenv("RNNT_B200_CHUNK_TPR"); return e ? atoi(e) : 0; }();
+    int tpr = pick_tpr(d.V);
+    if (forced_tpr == 1 || forced_tpr == 2 || forced_tpr == 4 || forced_tpr == 8) tpr = forced_tpr;   // tuning hook
     if (nt / tpr < 4) nt = 4 * tpr;   // a chunk is at least 4 rows (16-byte aligned chunk starts)
     const int rows_per = nt / tpr;
     const unsigned grid = (unsigned)(((uint64_t)d.rows + rows_per - 1) / rows_per);
     const size_t smem = (size_t)rows_per * d.V * sizeof(T);
     const bool scaled = scale != T(1) || scale_vec;
+    static const uint32_t wait_ns = [] { const char* e = getenv("RNNT_B200_CHUNK_WAIT_NS"); return e ? (uint32_t)atoi(e) : 2000u; }();
     static const int forced_map = [] { const char* e = getenv("RNNT_B200_CHUNK_MAP"); return e ? atoi(e) : -1; }();
     int hmajor = chunk_walk_cost(d.V, tpr, (int)sizeof(T), true) < chunk_walk_cost(d.V, tpr, (int)sizeof(T), false);
     if (forced_map == 0 || forced_map == 1) hmajor = forced_map;   // tuning hook
@@ -396,15 +402,15 @@ bool chunk_pass(const T* acts, T* grads, const int* labels, const int* xlen, con
         if constexpr (NT / TPR >= 4) {
             if (pass == 1)
                 prefer_smem(rowstats_chunk_kernel<T, TPR, NT>)<<<grid, NT, smem, s>>>(
-                    acts, labels, xlen, ylen, static_cast<Pair*>(w.stat), static_cast<Fac*>(w.lp2), d, hmajor);
+                    acts, labels, xlen, ylen, static_cast<Pair*>(w.stat), static_cast<Fac*>(w.lp2), d, hmajor, wait_ns);
             else if (scaled)
                 launch_k(prefer_smem(grad_chunk_kernel<T, TPR, NT, true>), dim3(grid), dim3(NT), smem, s, g_pdl, acts, grads,
                          labels, xlen, ylen, static_cast<const Pair*>(w.stat), static_cast<const Val*>(w.alphas),
-                         static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d, hmajor);
+                         static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d, hmajor, wait_ns);
             else
                 launch_k(prefer_smem(grad_chunk_kernel<T, TPR, NT, false>), dim3(grid), dim3(NT), smem, s, g_pdl, acts, grads,
                          labels, xlen, ylen, static_cast<const Pair*>(w.stat), static_cast<const Val*>(w.alphas),
-                         static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d, hmajor);
+                         static_cast<const Val*>(w.betas), static_cast<const Val*>(w.llf), scale, scale_vec, d, hmajor, wait_ns);
         }
     };
     auto with_rpt = [&](auto tpr_c) {
@@ -767,6 +773,8 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     const uint64_t rows64 = (uint64_t)N * T * U;
     if (rows64 >= (1ull << 31) || U > 1024 || opt.blank_label < 0 || opt.blank_label >= V)
         return RNNT_STATUS_INVALID_VALUE;
+    // the contraction kernels index inside one utterance's factor with 32-bit offsets
+    if ((uint64_t)std::max(T, U) * (uint64_t)V >= (1ull << 31)) return RNNT_STATUS_INVALID_VALUE;
     g_last_launches = 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(opt.stream);
     JointWorkspace w = carve_joint(workspace, N, T, U, V);
@@ -856,12 +864,25 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
             // 64-column accumulator tiles: small tensor-memory / shared-memory footprint -> several CTAs per SM,
             // and the whole tile's Ef fetches are in flight before the accumulator is read
             static const int df_tile = [] { const char* e = getenv("RNNT_B200_DF_TILE"); return e ? atoi(e) : 64; }();
+            static const bool fused = [] { const char* e = getenv("RNNT_B200_JOINT_FUSED"); return !(e && atoi(e) == 0); }();
+            if (fused && U <= 32) {
+                // both contractions in one pass over Ef (rnnt_umma.cuh: grad_fused_kernel)
+                const umma::GradFused gf{w.ef, w.eg, w.wm, dF, dG, T, U, V};
+                constexpr size_t smem = umma::GradFusedGeom<32, 32>::total;
+                auto go = [&](auto kernel) {
+                    func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kernel<<<dim3((unsigned)((V + 127) / 128), 1, (unsigned)N), umma::kThreads, smem, s>>>(gf);
+                };
+                if (V % 4 == 0) go(umma::grad_fused_kernel<32, 32, 3>);
+                else go(umma::grad_fused_kernel<32, 32, 0>);
+            } else {
             const umma::Epilogue epf{w.ef, (long long)T * V, 1, V, dF, 0, (long long)T * V, 1, V};
             if (V % 4 == 0) launch_umma<3, 1, 24>(EgT, WmTU, V, T, U, 1, N, epf, s, df_tile);   // 16-byte aligned rows
             else launch_umma<0, 1, 24>(EgT, WmTU, V, T, U, 1, N, epf, s, df_tile);
             const umma::Epilogue epg{w.eg, (long long)U * V, 1, V, dG, 0, (long long)U * V, 1, V};
             if (V % 4 == 0) launch_umma<3, 0, 24>(EfT, WmUT, V, U, T, 1, N, epg, s);
             else launch_umma<0, 0, 24>(EfT, WmUT, V, U, T, 1, N, epg, s);
+            }
         } else if (V >= 512) {  // long vocabulary: one thread per column, thin contraction
             {   // dF[t,v] = Ef[t,v] * sum_u Wm[t,u] Eg[u,v]
                 dim3 grid((V + 255) / 256, (T + kJointRT - 1) / kJointRT, N);

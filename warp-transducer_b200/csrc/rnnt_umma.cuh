@@ -10,9 +10,9 @@
 // lane v walks the accumulator's columns and its global accesses are coalesced across the warp.
 //
 // fp32 accuracy on tf32 tensor cores: every operand element x is split by the producer threads into
-// hi = tf32(x) (cvt.rna) and lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits), and
+// hi = tf32(x) (truncated) and lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits), and
 // each k-step issues three MMAs into the same accumulator: hi*hi + hi*lo + lo*hi.  The dropped lo*lo
-// term is 2^-22 relative; the sums feed a logarithm (S) and gradients checked to 1e-4 (P, Q).
+// term is 2^-20 relative; the sums feed a logarithm (S) and gradients checked to 1e-4 (P, Q).
 //
 // Operands are staged global -> registers (split) -> shared memory in the UMMA canonical K-major
 // NO-SWIZZLE ("interleave") layout, in units of 16-byte chunks (cute/atom/mma_traits_sm100.hpp:190-203):
@@ -27,6 +27,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace b200rnnt {
 namespace umma {
@@ -59,12 +60,15 @@ __device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// Spin on test_wait: a tensor-core commit arrives within a few hundred cycles.  (try_wait with a suspend-time
+// hint compiles to SYNCS.TRYWAIT + NANOSLEEP of the hint: with 1000 ns every wait for a ~0.3 us product was
+// rounded up to whole microseconds - measured: it WAS the run time of the contraction kernels.)
 __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+        asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done)
-                     : "r"(bar), "r"(parity), "r"(1000u)
+                     : "r"(bar), "r"(parity)
                      : "memory");
 }
 // 16 consecutive fp32 columns of this thread's accumulator lane
@@ -87,6 +91,17 @@ __host__ __device__ constexpr uint64_t smem_desc(uint32_t start_bytes, uint32_t 
     return (uint64_t)((start_bytes >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
 }
+// The same descriptor as two 32-bit words: only the start-address field (low word, bits [0,14)) changes
+// between the k-steps of a tile, so a kernel keeps one low word per tile and adds a constant per step.
+__host__ __device__ constexpr uint32_t smem_desc_lo(uint32_t start_bytes, uint32_t lbo_bytes) {
+    return ((start_bytes >> 4) & 0x3fff) | (((lbo_bytes >> 4) & 0x3fff) << 16);
+}
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fff) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
 // instruction descriptor for kind::tf32: D fp32 [4,6)=1, A tf32 [7,10)=2, B tf32 [10,13)=2,
 // a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N, bool a_mn, bool b_mn) {
@@ -103,7 +118,11 @@ constexpr int kPad = 144;   // padded stride between the 16-byte k-chunks of a r
 //  memory are transposed on their way into shared memory instead.)
 struct TileGeom {
     static __host__ __device__ constexpr uint32_t lbo() { return kPad; }
-    static __host__ __device__ constexpr uint32_t sbo(int KS) { return (uint32_t)(KS / 4) * kPad; }
+    // row-group stride: the k-chunks of a group plus a pad that makes it 16 (mod 128) bytes, so that 16-byte
+    // stores of 8 lanes to rows 4 apart in consecutive row groups (StageT4) fall on 8 different bank groups
+    static __host__ __device__ constexpr uint32_t sbo(int KS) {
+        return (uint32_t)(KS / 4) * kPad + (16u + 128u - ((uint32_t)(KS / 4) * kPad) % 128u) % 128u;
+    }
     static __host__ __device__ constexpr uint32_t bytes(int MN, int KS) { return (uint32_t)(MN / 8) * sbo(KS); }
     static __device__ __forceinline__ uint32_t off(int mn, int k, int KS) {
         return (uint32_t)(mn & 7) * 16 + (uint32_t)(mn >> 3) * sbo(KS) + (uint32_t)(k >> 2) * kPad + (uint32_t)(k & 3) * 4;
@@ -121,10 +140,10 @@ struct Operand {
     int mn_valid;
 };
 
+// hi = x truncated to tf32 (one LOP3; cvt.rna.tf32 is a four-instruction sequence on sm_100 and the staging
+// loops are issue-bound), lo = x - hi exactly; the tensor core then drops at most 2^-20 |x| from lo.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
     lo = x - hi;
 }
 
@@ -166,7 +185,7 @@ template <int MODE, int MN, int KS> struct StageRegs {
     float4 v4[(MODE == 2 || MODE == 3) ? PER : 1];
     float v1[(MODE == 2 || MODE == 3) ? 1 : PER];
     const float* g0;      // this thread's element 0 at k0 = 0
-    long long g_mn, g_k;  // global strides (elements) along mn / k
+    int g_mn, g_k;        // global strides (elements) along mn / k; offsets inside one batch item fit 32 bits
     uint32_t o0;          // shared-memory offset of element 0
     int mn_first, k_first, mn_lim;
 
@@ -189,7 +208,7 @@ template <int MODE, int MN, int KS> struct StageRegs {
             k_first = (MB >= 8 ? 0 : w / MB) * 4 + kk;
         }
         o0 = TileGeom::off(mn_first, k_first, KS);
-        g0 = base + (long long)(mn0 + mn_first) * g_mn + (long long)k_first * g_k;
+        g0 = base + ((mn0 + mn_first) * g_mn + k_first * g_k);
         mn_lim = op.mn_valid - mn0 - mn_first;   // element j is a real row iff its mn step < mn_lim
     }
     // (mn step, k step) of element j relative to element 0 - compile-time
@@ -204,13 +223,13 @@ template <int MODE, int MN, int KS> struct StageRegs {
                                                                   : 4 * KB_STEP * j;
     }
     __device__ __forceinline__ void load(int k0, int k_end) {
-        const float* g = g0 + (long long)k0 * g_k;
+        const float* g = g0 + k0 * g_k;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             const int kj = k0 + k_first + dk(j);
             const bool in = dmn(j) < mn_lim && kj < k_end && (MODE != 1 || k_first < KS) &&
                             (MODE == 2 ? mn_first + dmn(j) < MN : k_first + dk(j) < KS);
-            const float* p = g + (long long)dmn(j) * g_mn + (long long)dk(j) * g_k;
+            const float* p = g + (dmn(j) * g_mn + dk(j) * g_k);
             if (MODE == 3) {
                 v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (in) {
@@ -275,14 +294,84 @@ template <int MODE, int MN, int KS> struct StageRegs {
     }
 };
 
+// MN-contiguous operand with 16-byte aligned rows, transposed IN REGISTERS: a thread fetches a 4 (k) x 4 (mn)
+// block as four float4 loads (a warp: 32 adjacent blocks of one k group = four fully coalesced 512-byte row
+// pieces), and writes it as four 16-byte chunks per copy (one per mn: the four k values of a K-major chunk) -
+// 8 STS.128 instead of the 32 scalar stores of StageRegs MODE 3.  The hi / lo split here truncates
+// (hi = x & ~0x1fff, lo = x - hi, exact): one LOP3 instead of the four-instruction cvt.rna sequence; the
+// tensor core then drops at most 2^-20 of x from lo, instead of 2^-21 with rounding.
+// Same interface as StageRegs.  (ncu round 2: the fused gradient kernel executed 1080 warp instructions per
+// warp and 32-frame chunk, most of them in MODE 3 staging.)
+template <int MN, int KS> struct StageT4 {
+    static constexpr int MG = MN / 4, KG = KS / 4, UNITS = MG * KG;
+    static constexpr int PER = (UNITS + kThreads - 1) / kThreads;
+    static_assert(MN % 128 == 0 || MN == 32 || MN == 64, "a warp covers 32 adjacent blocks of one k group");
+    float4 v[PER][4];
+    const float* g0;
+    int g_k;
+    uint32_t o0;
+    int mn_lim, k_first;
+    bool active;
+    __device__ __forceinline__ void init(const Operand& op, const float* base, int mn0) {
+        const int tid = threadIdx.x;
+        const int mg = tid % MG, kg = tid / MG;
+        g_k = op.s_k;
+        k_first = 4 * kg;
+        active = tid < UNITS || PER > 1;
+        o0 = TileGeom::off(4 * mg, 4 * kg, KS);
+        g0 = base + (mn0 + 4 * mg + k_first * g_k);
+        mn_lim = op.mn_valid - mn0 - 4 * mg;   // > 0: the block's four rows exist (mn_valid is a multiple of 4)
+    }
+    __device__ __forceinline__ void load(int k0, int k_end) {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int kk = k_first + p * 4 * (kThreads / MG);
+            const float* gp = g0 + (k0 + p * 4 * (kThreads / MG)) * g_k;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool in = active && mn_lim > 0 && kk < KS && k0 + kk + j < k_end;
+                v[p][j] = in ? __ldg(reinterpret_cast<const float4*>(gp + j * g_k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    static __device__ __forceinline__ void split(float x, float& hi, float& lo) {
+        hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        lo = x - hi;
+    }
+    __device__ __forceinline__ void store(unsigned char* hi, unsigned char* lo) const {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int kk = k_first + p * 4 * (kThreads / MG);
+            if (!(active && mn_lim > 0 && kk < KS)) continue;
+            const uint32_t o = o0 + (uint32_t)(p * (kThreads / MG)) * kPad;
+            const float xs[4][4] = {{v[p][0].x, v[p][1].x, v[p][2].x, v[p][3].x},
+                                    {v[p][0].y, v[p][1].y, v[p][2].y, v[p][3].y},
+                                    {v[p][0].z, v[p][1].z, v[p][2].z, v[p][3].z},
+                                    {v[p][0].w, v[p][1].w, v[p][2].w, v[p][3].w}};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {   // row mn + c: one 16-byte chunk further inside the 8-row group
+                float4 h, l;
+                split(xs[c][0], h.x, l.x);
+                split(xs[c][1], h.y, l.y);
+                split(xs[c][2], h.z, l.z);
+                split(xs[c][3], h.w, l.w);
+                *reinterpret_cast<float4*>(hi + o + 16 * c) = h;
+                *reinterpret_cast<float4*>(lo + o + 16 * c) = l;
+            }
+        }
+    }
+};
+
 // What the epilogue does with accumulator element (m, n) of batch b, k slice `slice`:
 //   out[slice*out_s + b*out_b + m*out_m + n*out_n] = acc * (in ? in[b*in_b + m*in_m + n*in_n] : 1)
 // The `in` values of a group of columns are fetched before the accumulator is waited for.
 struct Epilogue {
     const float* in;
-    long long in_b, in_m, in_n;
+    long long in_b;
+    int in_m, in_n;      // strides inside one batch item: 32-bit
     float* out;
-    long long out_s, out_b, out_m, out_n;
+    long long out_s, out_b;
+    int out_m, out_n;
 };
 
 // D[128 x N] = sum_{k in slice} A[m0+m][k] * B[n0+n][k]   for batch blockIdx.z, M tile blockIdx.y, and
@@ -366,15 +455,15 @@ gemm_kernel(const Operand A, const Operand B, int K, int slices, const Epilogue 
     const int m = m0 + quarter * 32 + (threadIdx.x & 31);
     const bool mrow = m < A.mn_valid;
     constexpr int HALF = N / 2;
-    const float* ip = epi.in ? epi.in + b * epi.in_b + m * epi.in_m + (long long)(n0 + half * HALF) * epi.in_n : nullptr;
-    float* op = epi.out + slice * epi.out_s + b * epi.out_b + m * epi.out_m + (long long)(n0 + half * HALF) * epi.out_n;
+    const float* ip = epi.in ? epi.in + b * epi.in_b + (m * epi.in_m + (n0 + half * HALF) * epi.in_n) : nullptr;
+    float* op = epi.out + slice * epi.out_s + b * epi.out_b + (m * epi.out_m + (n0 + half * HALF) * epi.out_n);
     const int nlim = B.mn_valid - n0 - half * HALF;   // columns of this half that exist
     bool waited = false;
 #pragma unroll 1
     for (int c = 0; c < HALF; c += 16) {
         float pre[16], v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pre[i] = (ip && mrow && c + i < nlim) ? __ldg(ip + (long long)(c + i) * epi.in_n) : 1.0f;
+        for (int i = 0; i < 16; ++i) pre[i] = (ip && mrow && c + i < nlim) ? __ldg(ip + (c + i) * epi.in_n) : 1.0f;
         if (!waited) {
             // commits complete in issue order: the last stage's barrier covers all of them
             if (nstages > 0) bar_wait(s32(&mma_done[(nstages - 1) % kBufs]), (uint32_t)(((nstages - 1) / kBufs) & 1));
@@ -384,11 +473,200 @@ gemm_kernel(const Operand A, const Operand B, int K, int slices, const Epilogue 
         tmem_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * HALF + c), v);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (mrow && c + i < nlim) op[(long long)(c + i) * epi.out_n] = nstages > 0 ? v[i] * pre[i] : 0.0f;
+            if (mrow && c + i < nlim) op[(c + i) * epi.out_n] = nstages > 0 ? v[i] * pre[i] : 0.0f;
     }
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// =================================================================================================
+// Both gradient contractions of the additive joint in ONE pass over Ef (the [N,T,V] factor that dominates
+// the traffic).  CTA = (utterance b, 128 vocabulary entries v0..v0+127 = the accumulator lanes).  Time is
+// walked in chunks of TC frames; per chunk
+//
+//   Q[v,u] += sum_{t in chunk} Ef[t,v] Wm[t,u]        accumulates over all chunks     (K = t)
+//   P[v,t]  = sum_u            Eg[u,v] Wm[t,u]        complete after this chunk       (K = u, N = t in chunk)
+//   dF[t,v] = Ef[t,v] * P[v,t]                         written per chunk
+//
+// and after the last chunk  dG[u,v] = Eg[u,v] * Q[v,u].  Ef is read from DRAM once (the chunk's epilogue
+// re-reads the tile it has just staged - an L1/L2 hit) instead of once per contraction, and the P / Q products
+// of a chunk are issued back to back by one thread.  Tensor memory: Q in columns [0,NU), P (two buffers) behind it.
+// Shared memory: EgT (staged once), EfT / WmTU / WmUT of the current chunk, each as hi and lo tf32 copies.
+// =================================================================================================
+struct GradFused {
+    const float *ef, *eg, *wm;   // [N,T,V], [N,U,V], [N,T,U]
+    float *dF, *dG;              // [N,T,V], [N,U,V]
+    int T, U, V;
+};
+template <int NU, int TC> struct GradFusedGeom {
+    static constexpr int KU = (NU <= 24 ? 24 : NU);   // k extent of the P product (labels), a multiple of 8
+    static constexpr uint32_t A1 = TileGeom::bytes(128, KU), A2 = TileGeom::bytes(128, TC);
+    static constexpr uint32_t B1 = TileGeom::bytes(TC, KU), B2 = TileGeom::bytes(NU, TC);
+    static constexpr uint32_t total = 2 * (A1 + A2 + B1 + B2);
+};
+template <int NU, int TC, int A_MODE>   // A_MODE 3: rows of Ef / Eg 16-byte aligned (V % 4 == 0), else 0
+__global__ void __launch_bounds__(kThreads, 2)
+grad_fused_kernel(const GradFused g) {
+    static_assert(NU == 32 && TC == 32, "instantiated shape: up to 32 label positions, 32 frames per chunk");
+    using G = GradFusedGeom<NU, TC>;
+    constexpr int KU = G::KU;
+    constexpr uint32_t TMEM_COLS = 128;   // Q [0,NU), P double-buffered [NU, NU + 2 TC)
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long mma_done;
+    __shared__ uint32_t tmem_base_slot;
+    unsigned char* a1_hi = smem;
+    unsigned char* a1_lo = a1_hi + G::A1;
+    unsigned char* a2_hi = a1_lo + G::A1;
+    unsigned char* a2_lo = a2_hi + G::A2;
+    unsigned char* b1_hi = a2_lo + G::A2;
+    unsigned char* b1_lo = b1_hi + G::B1;
+    unsigned char* b2_hi = b1_lo + G::B1;
+    unsigned char* b2_lo = b2_hi + G::B2;
+
+    const int b = blockIdx.z, v0 = blockIdx.x * 128;
+    const int T = g.T, U = g.U, V = g.V;
+    const int warp = threadIdx.x >> 5;
+    const float* ef_b = g.ef + (long long)b * T * V;
+    const float* eg_b = g.eg + (long long)b * U * V;
+    const float* wm_b = g.wm + (long long)b * T * U;
+    const Operand EgT{g.eg, 0, 1, V, V}, EfT{g.ef, 0, 1, V, V};
+    const Operand WmTU{g.wm, 0, U, 1, T};   // (n = t, k = u)
+    const Operand WmUT{g.wm, 0, 1, U, U};   // (n = u, k = t)
+    const int nchunks = (T + TC - 1) / TC;
+
+    typename std::conditional<A_MODE == 3, StageT4<128, KU>, StageRegs<0, 128, KU>>::type r_eg;
+    typename std::conditional<A_MODE == 3, StageT4<128, TC>, StageRegs<0, 128, TC>>::type r_ef;
+    StageRegs<1, TC, KU> r_w1;
+    StageRegs<0, NU, TC> r_w2;
+    // The CTA's whole Ef tile (T rows x 512 B) is requested into L2 up front: with one chunk of register
+    // prefetch per CTA and two CTAs per SM, only ~32 KB per SM were in flight and the kernel ran at DRAM
+    // LATENCY (~3 TB/s); after this the chunk loads are L2 hits and DRAM sees the whole tile at once.
+    {
+        const int segs = min(4, (V - v0 + 31) / 32);   // 128-byte pieces of this tile's rows
+        for (int i = threadIdx.x; i < T * 4; i += kThreads) {
+            const int t = i >> 2, sg = i & 3;
+            if (sg < segs) asm volatile("prefetch.global.L2 [%0];" ::"l"(ef_b + ((long long)t * V + v0 + sg * 32)));
+        }
+    }
+    r_eg.init(EgT, eg_b, v0);
+    r_ef.init(EfT, ef_b, v0);
+    r_w2.init(WmUT, wm_b, 0);
+    r_eg.load(0, U);
+    r_ef.load(0, T);
+    r_w1.init(WmTU, wm_b, 0);
+    r_w1.load(0, U);
+    r_w2.load(0, T);
+    if (warp == 0) tmem_alloc(s32(&tmem_base_slot), TMEM_COLS);
+    if (threadIdx.x == 0) bar_init(s32(&mma_done), 1);
+    r_eg.store(a1_hi, a1_lo);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_q = tmem_base_slot, tmem_p = tmem_base_slot + NU;
+    constexpr uint32_t idesc_q = instr_desc_tf32(128, NU, false, false);
+    constexpr uint32_t idesc_p = instr_desc_tf32(128, TC, false, false);
+
+    // low descriptor words of the eight operand tiles (the buffers never move)
+    const uint32_t d_a1h = smem_desc_lo(s32(a1_hi), kPad), d_a1l = smem_desc_lo(s32(a1_lo), kPad);
+    const uint32_t d_a2h = smem_desc_lo(s32(a2_hi), kPad), d_a2l = smem_desc_lo(s32(a2_lo), kPad);
+    const uint32_t d_b1h = smem_desc_lo(s32(b1_hi), kPad), d_b1l = smem_desc_lo(s32(b1_lo), kPad);
+    const uint32_t d_b2h = smem_desc_lo(s32(b2_hi), kPad), d_b2l = smem_desc_lo(s32(b2_lo), kPad);
+    // epilogue geometry: warps w and w+4 own accumulator lanes [32(w%4), +32) and 16 columns each
+    const int quarter = warp & 3, half = warp >> 2;
+    const int m = v0 + quarter * 32 + (threadIdx.x & 31);
+    const bool mrow = m < V;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+
+    // dF of chunk c: Ef values first (L1/L2 hits), then the accumulator (P buffer c & 1)
+    auto epilogue_p = [&](int c) {
+        const int tb = c * TC + half * 16;
+        const float* ip = ef_b + (tb * V + m);
+        float* op = g.dF + (long long)b * T * V + (tb * V + m);
+        float pre[16], v[16];
+        const uint32_t taddr = tmem_p + (uint32_t)((c & 1) * TC) + lane_addr + (uint32_t)(half * 16);
+        // (warp-uniform branch: tcgen05.ld is a warp-collective instruction)
+        if (__all_sync(0xffffffffu, mrow) && tb + 16 <= T) {   // the common case: every row and all 16 frames exist
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pre[i] = __ldg(ip + i * V);
+            tmem_ld16(taddr, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) op[i * V] = v[i] * pre[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pre[i] = (mrow && tb + i < T) ? __ldg(ip + i * V) : 0.0f;
+            tmem_ld16(taddr, v);   // (warp-collective: executed by every lane, rows that do not exist included)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (mrow && tb + i < T) op[i * V] = v[i] * pre[i];
+        }
+    };
+    // Software pipeline: the products of chunk c run on the tensor core while the threads write chunk c-1's
+    // dF (P is double-buffered in tensor memory) and the loads of chunk c+1 are in flight.
+    for (int c = 0; c < nchunks; ++c) {
+        const int t0 = c * TC;
+        if (c > 0) {   // chunk c-1's products have read the stage buffers and written P[(c-1)&1]
+            bar_wait(s32(&mma_done), (uint32_t)((c - 1) & 1));
+            fence_after();
+        }
+        r_ef.store(a2_hi, a2_lo);
+        r_w1.store(b1_hi, b1_lo);
+        r_w2.store(b2_hi, b2_lo);
+        if (c + 1 < nchunks) {
+            r_ef.load(t0 + TC, T);
+            r_w1.init(WmTU, wm_b, t0 + TC);
+            r_w1.load(0, U);
+            r_w2.load(t0 + TC, T);
+        }
+        fence_smem_async();
+        fence_before();          // epilogue c-2's tcgen05.ld of P[c&1] precede the barrier
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after();
+            const uint32_t tp = tmem_p + (uint32_t)((c & 1) * TC);
+#pragma unroll
+            for (int j = 0; j < TC / 8; ++j) {
+                constexpr uint32_t hi = smem_desc_hi(TileGeom::sbo(TC));
+                const uint32_t st = TileGeom::kstep(j) >> 4;
+                const uint64_t ah = desc64(d_a2h + st, hi), al = desc64(d_a2l + st, hi);
+                const uint64_t bh = desc64(d_b2h + st, hi), bl = desc64(d_b2l + st, hi);
+                mma_tf32(tmem_q, ah, bh, idesc_q, (c | j) != 0);
+                mma_tf32(tmem_q, ah, bl, idesc_q, 1);
+                mma_tf32(tmem_q, al, bh, idesc_q, 1);
+            }
+#pragma unroll
+            for (int j = 0; j < KU / 8; ++j) {
+                constexpr uint32_t hi = smem_desc_hi(TileGeom::sbo(KU));
+                const uint32_t st = TileGeom::kstep(j) >> 4;
+                const uint64_t ah = desc64(d_a1h + st, hi), al = desc64(d_a1l + st, hi);
+                const uint64_t bh = desc64(d_b1h + st, hi), bl = desc64(d_b1l + st, hi);
+                mma_tf32(tp, ah, bh, idesc_p, j != 0);
+                mma_tf32(tp, ah, bl, idesc_p, 1);
+                mma_tf32(tp, al, bh, idesc_p, 1);
+            }
+            mma_commit(s32(&mma_done));
+        }
+        if (c > 0) epilogue_p(c - 1);
+    }
+    bar_wait(s32(&mma_done), (uint32_t)((nchunks - 1) & 1));
+    fence_after();
+    epilogue_p(nchunks - 1);
+    // dG: Q is complete (the last commit covered every product)
+    {
+        const int ub = half * 16;
+        const float* ip = eg_b + (ub * V + m);
+        float* op = g.dG + (long long)b * U * V + (ub * V + m);
+        float pre[16], v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pre[i] = (mrow && ub + i < U) ? __ldg(ip + i * V) : 0.0f;
+        tmem_ld16(tmem_q + lane_addr + (uint32_t)ub, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (mrow && ub + i < U) op[i * V] = v[i] * pre[i];
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_slot, TMEM_COLS);
 }
 
 template <int N, int KS>
