@@ -493,7 +493,11 @@ def other_workloads_leg(torch, wr, dev, peaks):
                         "algorithmic_GBps": bytes_ / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": bytes_ / (ms * 1e-3) / 1e9 / hbm,
                         "frac_of_8TBps": bytes_ / (ms * 1e-3) / 1e9 / 8000.0,
                         "kernel_ms": {"rowstats": kms[0], "lattice": kms[1], "grad": kms[2],
-                                      "note": "separate pass with event markers between the kernels (no launch overlap)"},
+                                      "note": ("this shape runs as 4 overlapped batch groups (a group's wavefront on a side stream beside "
+                                               "the streaming passes of the others): rowstats = pass 1 of all groups with the co-running "
+                                               "wavefronts, lattice = only the exposed wait before the first pass 2, grad = pass 2 of all "
+                                               "groups; the whole kernels alone (RNNT_B200_GROUPS=1) are in profiles/r2_c4_full.md")
+                                      if key == "c4" else "separate pass with event markers between the kernels (no launch overlap)"},
                         "l2": "flushed before every step" if small else "inputs exceed L2"}
             del sh
         except Exception as ex:

@@ -37,7 +37,7 @@ for dt in (torch.bfloat16, torch.float16):
     RNNTLoss()(acts, labels, tl, ul).backward()
     torch.cuda.synchronize()
     print(dt, "finite", bool(torch.isfinite(acts.grad.float()).all()))
-for (N, T, U, V) in [(2, 9, 5, 28), (2, 20, 34, 700)]:
+for (N, T, U, V) in [(2, 9, 5, 28), (2, 20, 34, 700), (2, 40, 7, 130), (2, 70, 21, 520)]:
     trans = torch.tensor(rng.standard_normal((N, T, V)).astype(np.float32), device=dev, requires_grad=True)
     pred = torch.tensor(rng.standard_normal((N, U, V)).astype(np.float32), device=dev, requires_grad=True)
     labels = torch.as_tensor(rng.integers(1, V, size=(N, U - 1)).astype(np.int32)).to(dev)

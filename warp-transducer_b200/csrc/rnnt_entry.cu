@@ -726,7 +726,7 @@ JointWorkspace carve_joint(void* base, int N, int T, int U, int V) {
     w.mf = static_cast<float*>(take((size_t)N * T * 4));
     w.mg = static_cast<float*>(take((size_t)N * U * 4));
     w.inv_s = static_cast<float*>(take(C * 4));
-    w.wm = static_cast<float*>(take(C * 4));
+    w.wm = static_cast<float*>(take(std::max(C, (size_t)N * T * umma::kWmPad) * 4));   // rows padded for the fused gradient kernel
     w.bk = static_cast<float*>(take(C * 4));
     w.lb = static_cast<float*>(take(C * 4));
     w.part = static_cast<float*>(take(C * 4 * kJointSlices));
@@ -852,8 +852,12 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     g_last_launches += 5;
     }  // phase != kBackward
     if (want_grad) {
-        joint_weights_kernel<<<(d.rows + 255) / 256, 256, 0, s>>>(w.lp2, w.alphas, w.betas, w.llf, w.inv_s,
-                                                                 xlen, ylen, w.wm, w.bk, w.lb, scale, scale_vec, d);
+        static const bool fused = [] { const char* e = getenv("RNNT_B200_JOINT_FUSED"); return !(e && atoi(e) == 0); }();
+        const bool use_fused = fused && joint_umma_enabled() && U <= umma::kWmPad;
+        const int wm_pitch = use_fused ? umma::kWmPad : U;
+        const unsigned wm_entries = (unsigned)N * T * wm_pitch;
+        joint_weights_kernel<<<(wm_entries + 255) / 256, 256, 0, s>>>(w.lp2, w.alphas, w.betas, w.llf, w.inv_s, xlen, ylen,
+                                                                     w.wm, w.bk, w.lb, scale, scale_vec, d, wm_pitch);
         if (joint_umma_enabled()) {
             // tcgen05, vocabulary index on the accumulator lanes (coalesced epilogue):
             //   dF[t,v] = Ef[t,v] * sum_u Eg[u,v] Wm[t,u]      M = v, N = t, K = u
@@ -864,8 +868,7 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
             // 64-column accumulator tiles: small tensor-memory / shared-memory footprint -> several CTAs per SM,
             // and the whole tile's Ef fetches are in flight before the accumulator is read
             static const int df_tile = [] { const char* e = getenv("RNNT_B200_DF_TILE"); return e ? atoi(e) : 64; }();
-            static const bool fused = [] { const char* e = getenv("RNNT_B200_JOINT_FUSED"); return !(e && atoi(e) == 0); }();
-            if (fused && U <= 32) {
+            if (use_fused) {
                 // both contractions in one pass over Ef (rnnt_umma.cuh: grad_fused_kernel)
                 const umma::GradFused gf{w.ef, w.eg, w.wm, dF, dG, T, U, V};
                 constexpr size_t smem = umma::GradFusedGeom<32, 32>::total;

@@ -212,11 +212,18 @@ joint_weights_kernel(const float4* __restrict__ lp2, const LogVal* __restrict__ 
                      const float* __restrict__ inv_s, const int* __restrict__ xlen,
                      const int* __restrict__ ylen, float* __restrict__ Wm, float* __restrict__ Bk,
                      float* __restrict__ Lb, const float scale_in, const float* __restrict__ scale_vec,
-                     const Dims d) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= d.rows) return;
-    uint32_t bt, u, b, t;
-    d.divU.divmod(r, bt, u);
+                     const Dims d, const int wm_pitch) {
+    // Wm rows have `wm_pitch` >= maxU entries (zero beyond maxU: the tensor-core kernel fetches them as aligned
+    // float4 rows); Bk / Lb / inv_s are [N,T,maxU].  One thread per Wm entry.
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (uint32_t)d.N * d.maxT * wm_pitch) return;
+    const uint32_t bt = q / (uint32_t)wm_pitch, u = q % (uint32_t)wm_pitch;
+    if (u >= (uint32_t)d.maxU) {
+        Wm[q] = 0.0f;
+        return;
+    }
+    const uint32_t r = bt * d.maxU + u;
+    uint32_t b, t;
     d.divT.divmod(bt, b, t);
     int Tb, Ub;
     utt_extent(d, xlen, ylen, b, Tb, Ub);
@@ -243,7 +250,7 @@ joint_weights_kernel(const float4* __restrict__ lp2, const LogVal* __restrict__ 
             lb = scale * exp2f((float)(oe + bn.e) + (ol + bn.l) + lpl2);
         }
     }
-    Wm[r] = w;
+    Wm[q] = w;
     Bk[r] = bk;
     Lb[r] = lb;
 }

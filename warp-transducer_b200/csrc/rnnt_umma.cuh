@@ -495,12 +495,13 @@ gemm_kernel(const Operand A, const Operand B, int K, int slices, const Epilogue 
 // Shared memory: EgT (staged once), EfT / WmTU / WmUT of the current chunk, each as hi and lo tf32 copies.
 // =================================================================================================
 struct GradFused {
-    const float *ef, *eg, *wm;   // [N,T,V], [N,U,V], [N,T,U]
+    const float *ef, *eg, *wm;   // [N,T,V], [N,U,V], [N,T,kWmPad]: Wm rows zero-padded to kWmPad label positions
     float *dF, *dG;              // [N,T,V], [N,U,V]
     int T, U, V;
 };
+constexpr int kWmPad = 32;       // the weights' row pitch (16-byte aligned rows: both Wm operands are fetched as float4)
 template <int NU, int TC> struct GradFusedGeom {
-    static constexpr int KU = (NU <= 24 ? 24 : NU);   // k extent of the P product (labels), a multiple of 8
+    static constexpr int KU = NU;   // k extent of the P product (label positions, padded)
     static constexpr uint32_t A1 = TileGeom::bytes(128, KU), A2 = TileGeom::bytes(128, TC);
     static constexpr uint32_t B1 = TileGeom::bytes(TC, KU), B2 = TileGeom::bytes(NU, TC);
     static constexpr uint32_t total = 2 * (A1 + A2 + B1 + B2);
@@ -529,33 +530,23 @@ grad_fused_kernel(const GradFused g) {
     const int warp = threadIdx.x >> 5;
     const float* ef_b = g.ef + (long long)b * T * V;
     const float* eg_b = g.eg + (long long)b * U * V;
-    const float* wm_b = g.wm + (long long)b * T * U;
+    const float* wm_b = g.wm + (long long)b * T * kWmPad;
     const Operand EgT{g.eg, 0, 1, V, V}, EfT{g.ef, 0, 1, V, V};
-    const Operand WmTU{g.wm, 0, U, 1, T};   // (n = t, k = u)
-    const Operand WmUT{g.wm, 0, 1, U, U};   // (n = u, k = t)
+    const Operand WmTU{g.wm, 0, kWmPad, 1, T};        // (n = t, k = u): k-contiguous, aligned rows
+    const Operand WmUT{g.wm, 0, 1, kWmPad, kWmPad};   // (n = u, k = t): n-contiguous, transposed in registers
     const int nchunks = (T + TC - 1) / TC;
 
     typename std::conditional<A_MODE == 3, StageT4<128, KU>, StageRegs<0, 128, KU>>::type r_eg;
     typename std::conditional<A_MODE == 3, StageT4<128, TC>, StageRegs<0, 128, TC>>::type r_ef;
-    StageRegs<1, TC, KU> r_w1;
-    StageRegs<0, NU, TC> r_w2;
-    // The CTA's whole Ef tile (T rows x 512 B) is requested into L2 up front: with one chunk of register
-    // prefetch per CTA and two CTAs per SM, only ~32 KB per SM were in flight and the kernel ran at DRAM
-    // LATENCY (~3 TB/s); after this the chunk loads are L2 hits and DRAM sees the whole tile at once.
-    {
-        const int segs = min(4, (V - v0 + 31) / 32);   // 128-byte pieces of this tile's rows
-        for (int i = threadIdx.x; i < T * 4; i += kThreads) {
-            const int t = i >> 2, sg = i & 3;
-            if (sg < segs) asm volatile("prefetch.global.L2 [%0];" ::"l"(ef_b + ((long long)t * V + v0 + sg * 32)));
-        }
-    }
+    StageRegs<2, TC, KU> r_w1;   // one float4 per thread
+    StageT4<NU, TC> r_w2;        // 64 threads, a 4x4 block each
     r_eg.init(EgT, eg_b, v0);
     r_ef.init(EfT, ef_b, v0);
     r_w2.init(WmUT, wm_b, 0);
     r_eg.load(0, U);
     r_ef.load(0, T);
     r_w1.init(WmTU, wm_b, 0);
-    r_w1.load(0, U);
+    r_w1.load(0, kWmPad);
     r_w2.load(0, T);
     if (warp == 0) tmem_alloc(s32(&tmem_base_slot), TMEM_COLS);
     if (threadIdx.x == 0) bar_init(s32(&mma_done), 1);
@@ -615,7 +606,7 @@ grad_fused_kernel(const GradFused g) {
         if (c + 1 < nchunks) {
             r_ef.load(t0 + TC, T);
             r_w1.init(WmTU, wm_b, t0 + TC);
-            r_w1.load(0, U);
+            r_w1.load(0, kWmPad);
             r_w2.load(t0 + TC, T);
         }
         fence_smem_async();
