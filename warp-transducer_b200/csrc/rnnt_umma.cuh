@@ -224,6 +224,16 @@ template <int MODE, int MN, int KS> struct StageRegs {
     }
     __device__ __forceinline__ void load(int k0, int k_end) {
         const float* g = g0 + k0 * g_k;
+        if (MODE == 2 && k0 + KS <= k_end) {
+            // every stage but the last of a k range: no k raggedness - one predicated 16-byte load per row
+            // (CTA-uniform branch; the general form below costs ~3x the instructions in an issue-bound loop)
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const bool in = dmn(j) < mn_lim && mn_first + dmn(j) < MN;
+                v4[j] = in ? __ldg(reinterpret_cast<const float4*>(g + dmn(j) * g_mn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             const int kj = k0 + k_first + dk(j);
