@@ -17,7 +17,12 @@ def reference(trans, pred, labels, tl, ul, blank):
 
 
 @pytest.mark.parametrize("shape", [(3, 9, 5, 28, 0), (2, 17, 34, 13, 4), (4, 30, 8, 300, 0),
-                                   (2, 6, 3, 5000, 7), (3, 12, 1, 9, 0), (2, 1, 4, 6, 0), (5, 70, 66, 50, 0)],
+                                   (2, 6, 3, 5000, 7), (3, 12, 1, 9, 0), (2, 1, 4, 6, 0), (5, 70, 66, 50, 0),
+                                   (2, 33, 32, 130, 0),    # fused gradient kernel: 32 label positions, 2 chunks, V % 4 != 0
+                                   (2, 70, 21, 520, 3),    # fused: 3 chunks, 5 vocabulary tiles (the last with 8 rows)
+                                   (2, 40, 33, 64, 0),     # 33 label positions: the two-kernel gradient path
+                                   (2, 6, 20, 3, 0),       # V = 3: almost every label repeats (sparse terms)
+                                   (1, 1, 2, 4, 0)],
                          ids=lambda s: "N%d_T%d_U%d_V%d_b%d" % s)
 def test_add_joint_matches_dense_oracle(shape):
     from warprnnt_pytorch.joint import AddJointRNNTLoss

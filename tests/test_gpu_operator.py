@@ -233,7 +233,7 @@ def test_sixteen_bit_storage(dtype):
     from warprnnt_pytorch import RNNTLoss, warp_rnnt as wr
     rng = np.random.default_rng(13)
     eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
-    for (N, T, U, V) in [(3, 11, 5, 64), (2, 7, 4, 5000), (2, 6, 3, 37), (2, 9, 34, 16)]:
+    for (N, T, U, V) in [(3, 11, 5, 64), (2, 7, 4, 5000), (2, 6, 3, 37), (2, 9, 34, 16), (2, 5, 3, 4100), (1, 4, 2, 5001)]:
         acts_t = torch.tensor(rng.standard_normal((N, T, U, V)).astype(np.float32)).to(dtype)
         acts_np = acts_t.float().numpy()                      # the rounded logits the kernel sees
         labels_np = rng.integers(1, V, size=(N, U - 1)).astype(np.int32)

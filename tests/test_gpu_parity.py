@@ -168,6 +168,11 @@ SHAPES = [
     (2, 9, 70, 4, 0),      # 3 warps
     (1, 3, 800, 4, 0),     # 25 warps: cp.async ring above 48 KB (shared-memory opt-in)
     (1, 2, 1024, 3, 0),    # the maximum label extent (same limit as the reference's launch)
+    (2, 1, 70, 4, 0),      # multi-warp wavefront with a single frame: only the store delay line's drain writes
+    (2, 3, 129, 5, 0),     # 5 warps, fewer steps per column than the delay line is deep
+    (3, 40, 65, 50, 0),    # 3 warps, ragged, short-row (chunk) streaming kernels at V=50
+    (2, 12, 41, 28, 0),    # one warp x two columns per lane (33..64 labels), chunk kernels at V=28
+    (2, 9, 64, 4, 0),      # exactly 64 labels: the last single-warp shape
     (3, 40, 1, 6, 0),      # U == 1: empty label sequences
     (3, 1, 5, 6, 0),       # T == 1
     (1, 1, 1, 4, 0),       # single cell
