@@ -704,7 +704,11 @@ rnntStatus_t run(const IO* acts, IO* grads, const int* labels, const int* ylen, 
 
 // ---- additive-joint variant (rnnt_joint.cuh) ----------------------------------------------------
 constexpr int kJointSlices = 16;  // max split-K slabs of the S = Ef.Eg^T contraction (K = V is the long axis)
-inline int joint_slices(int V) { return std::max(1, std::min(kJointSlices, V / 320)); }
+inline int joint_slices(int V) {
+    static const int forced = [] { const char* e = getenv("RNNT_B200_JOINT_SLICES"); return e ? atoi(e) : 0; }();
+    if (forced >= 1 && forced <= kJointSlices) return forced;   // tuning hook
+    return std::max(1, std::min(kJointSlices, V / 320));
+}
 struct JointWorkspace {
     float *ef, *eg, *mf, *mg, *inv_s, *wm, *bk, *lb, *part;
     float4* lp2;
@@ -871,7 +875,8 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
             if (use_fused) {
                 // both contractions in one pass over Ef (rnnt_umma.cuh: grad_fused_kernel)
                 const umma::GradFused gf{w.ef, w.eg, w.wm, dF, dG, T, U, V};
-                constexpr size_t smem = umma::GradFusedGeom<32, 32>::total;
+                static const size_t pad = [] { const char* e = getenv("RNNT_B200_FUSED_PAD_SMEM"); return e ? (size_t)atoi(e) : (size_t)0; }();
+                const size_t smem = umma::GradFusedGeom<32, 32>::total + pad;   // pad: residency experiment hook
                 auto go = [&](auto kernel) {
                     func_attr_once(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     kernel<<<dim3((unsigned)((V + 127) / 128), 1, (unsigned)N), umma::kThreads, smem, s>>>(gf);
