@@ -1,2 +1,6 @@
+# Dev helper: what one `gpurun -- bash tools/run_gpu_check.sh` call checks after a kernel change.
 set -x
-for P in 0 60000; do RNNT_B200_FUSED_PAD_SMEM=$P timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file /tmp/lj.csv python tools/joint_profile_target.py > /dev/null 2>&1; grep -i "grad_fused" /tmp/lj.csv | cut -d, -f5,12- | cut -c1-160 | tail -1; done
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -5
+timeout 300 python tools/unprofiled_time.py            # c2 / c4 / c3, device time of the async C-ABI
+timeout 300 python tools/quick_time.py --bf16 c3 2>&1 | grep "loss+grad"
+timeout 300 python tools/joint_time.py 2>&1 | tail -3
