@@ -163,3 +163,46 @@ def test_tensorflow_op_call_sequence(wr, known_answers):
     assert st == 0
     assert np.allclose(costs, ka["costs"], atol=1e-6)                  # readable right after the call
     assert np.allclose(grads.cpu().numpy().reshape(-1), ka["logits_grads"], atol=1e-6)   # the TF test's tolerance
+
+
+def test_every_gradient_element_is_written():
+    """The library writes EVERY element of the gradient tensors (zeros on padding, no memset pass):
+    buffers pre-filled with NaN must come back NaN-free - every kernel family, ragged lengths, the
+    training-step split, 16-bit storage, fp64, and both additive-joint gradient paths."""
+    import torch
+    from warprnnt_pytorch import warp_rnnt as w
+    from warprnnt_pytorch.joint import add_joint_call
+    rng = np.random.default_rng(5)
+    dev = torch.device("cuda:0")
+    shapes = [(3, 9, 5, 28), (2, 12, 40, 6), (2, 7, 4, 301), (2, 5, 3, 1028), (1, 3, 2, 8200), (9, 30, 70, 50),
+              (4, 33, 9, 50), (3, 10, 3, 64), (2, 6, 4, 5000), (2, 3, 129, 5)]
+    for dt in (torch.float32, torch.float64, torch.bfloat16):
+        for (N, T, U, V) in shapes:
+            if dt != torch.float32 and V > 2000 and U > 4:
+                continue
+            acts = torch.tensor(rng.standard_normal((N, T, U, V)).astype(np.float32), device=dev).to(dt)
+            labels = torch.as_tensor(rng.integers(1, V, size=(N, U - 1)).astype(np.int32)).to(dev)
+            tl = torch.as_tensor(rng.integers(T // 2 + 1, T + 1, size=N).astype(np.int32)).to(dev)
+            ul = torch.as_tensor(rng.integers(0, U, size=N).astype(np.int32)).to(dev)
+            costs = torch.empty(N, device=dev, dtype=torch.float64 if dt == torch.float64 else torch.float32)
+            grads = torch.full_like(acts, float("nan"))
+            w.gpu_rnnt_async(acts, labels, tl, ul, costs, grads, 0)
+            torch.cuda.synchronize()
+            assert not torch.isnan(grads.float()).any(), ("full", dt, (N, T, U, V))
+            grads = torch.full_like(acts, float("nan"))
+            ws = w.gpu_rnnt_forward(acts, labels, tl, ul, costs, 0, True)
+            w.gpu_rnnt_backward(acts, labels, tl, ul, grads, None, 0, 0.5, ws)
+            torch.cuda.synchronize()
+            assert not torch.isnan(grads.float()).any(), ("split", dt, (N, T, U, V))
+    for (N, T, U, V) in [(2, 9, 5, 28), (2, 20, 34, 700), (2, 40, 7, 130), (2, 70, 21, 520), (3, 33, 32, 64)]:
+        trans = torch.tensor(rng.standard_normal((N, T, V)).astype(np.float32), device=dev)
+        pred = torch.tensor(rng.standard_normal((N, U, V)).astype(np.float32), device=dev)
+        labels = torch.as_tensor(rng.integers(1, V, size=(N, U - 1)).astype(np.int32)).to(dev)
+        tl = torch.as_tensor(rng.integers(T // 2 + 1, T + 1, size=N).astype(np.int32)).to(dev)
+        ul = torch.as_tensor(rng.integers(0, U, size=N).astype(np.int32)).to(dev)
+        costs = torch.empty(N, device=dev)
+        dtrans, dpred = torch.full_like(trans, float("nan")), torch.full_like(pred, float("nan"))
+        ws = add_joint_call(trans, pred, labels, tl, ul, costs, dtrans, dpred, 0, 1.0)
+        torch.cuda.synchronize()
+        assert not torch.isnan(dtrans).any() and not torch.isnan(dpred).any(), ("joint", (N, T, U, V))
+        del ws
