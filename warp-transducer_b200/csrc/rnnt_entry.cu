@@ -857,7 +857,8 @@ rnntStatus_t run_add_joint(const float* f, const float* g, float* dF, float* dG,
     }  // phase != kBackward
     if (want_grad) {
         static const bool fused = [] { const char* e = getenv("RNNT_B200_JOINT_FUSED"); return !(e && atoi(e) == 0); }();
-        const bool use_fused = fused && joint_umma_enabled() && U <= umma::kWmPad;
+        const bool use_fused = fused && joint_umma_enabled() && U <= umma::kWmPad &&
+                               (uint64_t)N * T * umma::kWmPad < (1ull << 31);   // padded weights are indexed with 32 bits
         const int wm_pitch = use_fused ? umma::kWmPad : U;
         const unsigned wm_entries = (unsigned)N * T * wm_pitch;
         joint_weights_kernel<<<(wm_entries + 255) / 256, 256, 0, s>>>(w.lp2, w.alphas, w.betas, w.llf, w.inv_s, xlen, ylen,
