@@ -297,3 +297,32 @@ def test_concurrent_host_threads():
         t.join()
     assert not errors, errors
     assert all(results.get(i) for i in range(len(shapes))), results
+
+
+def test_length_checks_on_cuda_tensors_raise_and_leave_the_device_usable():
+    """The T / U consistency test of certify_inputs is waited for AFTER the kernels are queued (LengthCheck);
+    it must still raise from the same call, a labels tensor narrower than U-1 must never reach a kernel,
+    and the device must be usable afterwards."""
+    from warprnnt_pytorch import RNNTLoss
+    rng = np.random.default_rng(3)
+    N, T, U, V = 3, 9, 5, 17
+    acts = torch.tensor(rng.standard_normal((N, T, U, V)).astype(np.float32), device="cuda", requires_grad=True)
+    labels = torch.as_tensor(rng.integers(1, V, size=(N, U - 1)).astype(np.int32)).cuda()
+    tl = torch.tensor([T, 7, 5], dtype=torch.int32).cuda()
+    ul = torch.tensor([U - 1, 2, 0], dtype=torch.int32).cuda()
+    f = RNNTLoss(reduction='sum')
+    with pytest.raises(ValueError, match="Input length mismatch"):
+        f(acts, labels, torch.tensor([T - 1, 7, 5], dtype=torch.int32).cuda(), ul)
+    with pytest.raises(ValueError, match="Input length mismatch"):
+        f(acts, labels, torch.tensor([T + 3, 7, 5], dtype=torch.int32).cuda(), ul)     # longer than the tensor: clamped
+    with pytest.raises(ValueError, match="Output length mismatch"):
+        f(acts, labels, tl, torch.tensor([U - 2, 2, 0], dtype=torch.int32).cuda())
+    with pytest.raises(ValueError):
+        f(acts, labels[:, :2].contiguous(), tl, ul)                                     # labels narrower than U-1
+    loss = f(acts, labels, tl, ul)
+    loss.backward()
+    torch.cuda.synchronize()
+    c_ref, g_ref, _ = pyoracle.rnnt_logits(acts.detach().cpu().numpy().astype(np.float64), labels.cpu().numpy(),
+                                           tl.cpu().numpy(), ul.cpu().numpy(), 0)
+    assert np.allclose(loss.item(), c_ref.sum(), rtol=1e-5)
+    assert np.allclose(acts.grad.cpu().numpy(), g_ref, rtol=1e-4, atol=1e-6)

@@ -32,7 +32,7 @@ class _RNNT(Function):
         labels: (batch x maxLabelLength) int32 targets, zero padded
         act_lens / label_lens: (batch) int32
         """
-        certify_inputs(acts, labels, act_lens, label_lens)
+        length_check = certify_inputs(acts, labels, act_lens, label_lens, defer=True)
         if not acts.is_cuda:
             raise RuntimeError("warprnnt_pytorch (B200 build) runs on CUDA tensors only; "
                                "there is no CPU fallback")
@@ -40,11 +40,13 @@ class _RNNT(Function):
         if reduction not in ('none', 'sum', 'mean'):
             raise ValueError("reduction must be 'none', 'sum' or 'mean'")
         minibatch_size = acts.size(0)
+        length_check.guard_labels(labels, minibatch_size)
         need_grad = acts.requires_grad
         # bf16 / fp16 logits: arithmetic, lattice and costs are fp32 (6 B per logit instead of 12)
         costs = torch.empty(minibatch_size, dtype=warp_rnnt.costs_dtype(acts), device=acts.device)
         ws = warp_rnnt.gpu_rnnt_forward(acts, labels, act_lens, label_lens, costs, blank,
                                         prepare_backward=need_grad)
+        length_check.finish()   # T == max(act_lens), U == max(label_lens) + 1: waited for with the kernels queued
         if need_grad:
             ctx.save_for_backward(acts, labels, act_lens, label_lens)
             ctx.workspace = ws

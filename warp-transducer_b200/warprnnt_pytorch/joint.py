@@ -16,7 +16,7 @@ from torch.autograd import Function
 from torch.nn import Module
 
 from . import warp_rnnt
-from ._checks import check_contiguous, check_dim, check_type
+from ._checks import LengthCheck, check_contiguous, check_dim, check_type
 
 _lib = warp_rnnt.lib()
 _P = C.c_void_p
@@ -33,7 +33,7 @@ _lib.rnnt_b200_add_joint_workspace_size.restype = C.c_int
 _lib.rnnt_b200_add_joint_workspace_size.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
 
 
-def certify_joint_inputs(trans, pred, labels, lengths, label_lengths):
+def certify_joint_inputs(trans, pred, labels, lengths, label_lengths, defer=False):
     check_type(labels, torch.int32, "labels")
     check_type(label_lengths, torch.int32, "label_lengths")
     check_type(lengths, torch.int32, "lengths")
@@ -49,11 +49,11 @@ def certify_joint_inputs(trans, pred, labels, lengths, label_lengths):
         raise ValueError("must have a length and a label length per example.")
     if trans.shape[2] != pred.shape[2]:
         raise ValueError("trans and pred must share the vocabulary dimension")
-    max_T, max_U = torch.stack((lengths.max(), label_lengths.max())).tolist()
-    if trans.shape[1] != max_T:
-        raise ValueError("Input length mismatch")
-    if pred.shape[1] != max_U + 1:
-        raise ValueError("Output length mismatch")
+    check = LengthCheck(lengths, label_lengths, trans.shape[1], pred.shape[1])
+    if defer:
+        return check
+    check.finish()
+    return None
 
 
 def add_joint_call(trans, pred, labels, act_lens, label_lens, costs, dtrans, dpred, blank, scale):
@@ -95,7 +95,7 @@ class _AddJointRNNT(Function):
 
     @staticmethod
     def forward(ctx, trans, pred, labels, act_lens, label_lens, blank, reduction):
-        certify_joint_inputs(trans, pred, labels, act_lens, label_lens)
+        length_check = certify_joint_inputs(trans, pred, labels, act_lens, label_lens, defer=True)
         if not trans.is_cuda:
             raise RuntimeError("warprnnt_pytorch (B200 build) runs on CUDA tensors only")
         warp_rnnt.require_same_device(trans, pred=pred, labels=labels, act_lens=act_lens, label_lens=label_lens)
@@ -103,6 +103,7 @@ class _AddJointRNNT(Function):
             raise ValueError("reduction must be 'none', 'sum' or 'mean'")
         N, T, V = trans.shape
         U = pred.shape[1]
+        length_check.guard_labels(labels, N)
         need = trans.requires_grad or pred.requires_grad
         costs = torch.empty(N, dtype=torch.float32, device=trans.device)
         n = C.c_size_t(0)
@@ -115,6 +116,7 @@ class _AddJointRNNT(Function):
                                                   _joint_opts(trans, pred, blank))
         if st != 0:
             raise RuntimeError("rnnt_b200_add_joint_forward failed: " + warp_rnnt.status_string(st))
+        length_check.finish()   # the reference's length test, waited for with the kernels already queued
         if need:
             ctx.save_for_backward(trans, pred, labels, act_lens, label_lens)
             ctx.ws, ctx.blank = ws, blank
