@@ -22,6 +22,10 @@
 // warp therefore settles a step or two behind its upstream neighbour and the shared-memory round trip
 // leaves the dependent chain; there is no __syncthreads in the step loop.
 //
+// Layouts: the factors are read diagonal-major (one 16-byte cp.async per lane and step, contiguous across
+// the lanes); alpha / beta are written CELL-major [b][t][u] for the gradient pass (rnnt_kernels.cuh: cell()),
+// directly by single-warp wavefronts and through a per-lane delay line by multi-warp ones (see the body).
+//
 // Replaces reference compute_alphas_kernel / compute_betas_kernel (gpu_rnnt_kernel.h:11-47,79-113)
 // and log_sum_exp (rnnt_helper.h:16-24) for fp32.
 #pragma once

@@ -21,9 +21,10 @@
 // padded (144 B instead of 128 B) so that the scalar stores of a warp hit 32 different banks.
 //
 // One CTA = 256 threads = 8 warps, two per lane quarter of the 128-lane accumulator.  All threads
-// produce the k-stages (double-buffered, next stage's loads in flight in registers), thread 0 issues the
-// MMAs of a stage and commits them to that buffer's mbarrier; the epilogue reads the accumulator with
-// tcgen05.ld.
+// produce the k-stages (one shared-memory stage buffer, the next stage's loads in flight in registers),
+// thread 0 issues the MMAs of a stage and commits them to the mbarrier; the epilogue reads the
+// accumulator with tcgen05.ld.  gemm_kernel is the generic form (S, and dF / dG beyond 32 label positions);
+// grad_fused_kernel computes P and Q in one pass over Ef (see there).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
