@@ -167,7 +167,8 @@ SidePool& side_pool() {
 struct Workspace {
     void* stat;     // pair<T>  [rows]   (row max, log sum exp)
     void* lp2;      // Lat<T>::fac [lat]  per-cell transition factors (16 B), diagonal-major
-    void* alphas;   // Lat<T>::val [lat]  lat = N*(maxT+maxU-1)*maxU   (8 B: LogVal for fp32, double for fp64)
+    void* alphas;   // Lat<T>::val [lat]  lat = N*(maxT+maxU-1)*maxU   (8 B: LogVal for fp32 - cell-major, using N*maxT*maxU
+                    //                    of the entries -, double for fp64 - diagonal-major)
     void* betas;    // Lat<T>::val [lat]
     void* llf;      // Lat<T>::val [N]
     void* llb;      // Lat<T>::val [N]

@@ -39,7 +39,7 @@ struct Dims {
     }
 };
 
-// The lattice arrays (lp2, alphas, betas) are stored DIAGONAL-MAJOR per utterance: cell (t,u)
+// The factor array lp2 (and, on the fp64 path, alphas / betas) is stored DIAGONAL-MAJOR per utterance: cell (t,u)
 // lives at (t+u)*maxU + u inside a block of (maxT+maxU-1)*maxU entries.  The wavefront kernel
 // touches one anti-diagonal per step, so its loads and stores are contiguous across the u-threads
 // (one or two 128-B lines per warp instead of 32 scattered sectors in the row-major form).
