@@ -271,6 +271,14 @@ int rnnt_b200_last_kernel_ms(float* ms3);
  * Lets a timed loop run without any host synchronisation between steps. */
 int rnnt_b200_profile_collect(float* ms3_mean);
 
+/* Host-side dispatch policy, for tests and tuning notes (no device access).  `what`:
+ *   0  lanes sharing one short row in the chunk kernels for alphabet size a and element size b bytes (0: row too long
+ *      for the chunk kernels);  1  1 if those lanes are `32 / lanes` apart in the warp (bank-aware mapping), 0 if adjacent;
+ *   2  label columns per lane of the fp32 wavefront for maxU = a;  3  its threads per utterance and direction;
+ *   4  diagonals of its factor ring (b != 0: next to the streaming passes of other batch groups);
+ *   5  split-K slabs of the additive joint's S product for alphabet size a.   Returns -1 for an unknown `what`. */
+int rnnt_b200_debug_policy(int what, int a, int b);
+
 /* Build identification string, e.g. "b200-rnnt sm_100a <date>". */
 const char* rnnt_b200_build_info(void);
 

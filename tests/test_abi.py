@@ -128,3 +128,22 @@ def test_operator_rejects_cpu_tensors_and_bad_inputs():
     with pytest.raises(ValueError):
         rnnt_loss(acts.transpose(1, 2), labels, tl, ul)   # not contiguous
     certify_inputs(acts, labels, tl, ul)
+
+
+def test_dispatch_policy_matches_the_design_notes(wr):
+    """Host-side shape policy: the values the measurements in profiles/ were taken with."""
+    lib = wr.lib()
+    lib.rnnt_b200_debug_policy.restype = C.c_int
+    lib.rnnt_b200_debug_policy.argtypes = [C.c_int, C.c_int, C.c_int]
+    f = lib.rnnt_b200_debug_policy
+    # chunk kernels: two lanes per row for the README short-vocabulary shapes, bank-aware (slice-major) mapping
+    assert f(0, 28, 4) == 2 and f(0, 50, 4) == 2 and f(0, 100, 4) == 4 and f(0, 29, 4) == 1
+    assert f(0, 129, 4) == 0 and f(0, 5000, 4) == 0 and f(0, 64, 8) == 2 and f(0, 65, 8) == 0
+    assert f(1, 50, 4) == 1 and f(1, 28, 4) == 0     # V=28 with two lanes per row is conflict-free either way
+    # wavefront: one warp up to 64 labels (two columns per lane from 33), one column per lane beyond
+    assert [f(2, u, 0) for u in (1, 21, 32, 33, 41, 64, 65, 301, 1024)] == [1, 1, 1, 2, 2, 2, 1, 1, 1]
+    assert [f(3, u, 0) for u in (21, 32, 33, 64, 65, 301, 1024)] == [32, 32, 32, 32, 96, 320, 1024]
+    # factor ring: 8 diagonals alone, deeper next to streaming passes while ~100 KB allow
+    assert f(4, 301, 0) == 8 and f(4, 301, 1) == 16 and f(4, 1024, 1) == 8 and f(4, 41, 1) == 8
+    assert f(5, 5000, 0) == 15 and f(5, 28, 0) == 1
+    assert f(99, 0, 0) == -1

@@ -1211,6 +1211,22 @@ int rnnt_b200_profile_collect(float* ms3_mean) {
     return calls;
 }
 
+int rnnt_b200_debug_policy(int what, int a, int b) {
+    switch (what) {
+        case 0: return (size_t)a * (size_t)b > 512 || a <= 0 ? 0 : pick_tpr(a);
+        case 1: {
+            if ((size_t)a * (size_t)b > 512 || a <= 0) return 0;
+            const int tpr = pick_tpr(a);
+            return chunk_walk_cost(a, tpr, b, true) < chunk_walk_cost(a, tpr, b, false) ? 1 : 0;
+        }
+        case 2: return lattice_cols(a);
+        case 3: return lattice_threads(a);
+        case 4: return lattice_ring_depth(a, b != 0);
+        case 5: return joint_slices(a);
+        default: return -1;
+    }
+}
+
 const char* rnnt_b200_build_info(void) { return "b200-rnnt sm_100a built " __DATE__ " " __TIME__; }
 
 }  // extern "C"
